@@ -1,0 +1,288 @@
+"""Canonical neighborhood partition - host side of the sm_100a kernels in csrc/partition.cu.
+
+Mirrors the partition surface of ``subgraph_counting/data.py`` (reference @ 4508f7a):
+
+    k_neigh / k_neigh_canonical          data.py:329-350
+    get_neigh_canonical / get_neigh_hetero  data.py:353-396   (nx.Graph in, nx.Graph out - drop-in signatures)
+
+and adds the batched entry point the datasets use (``partition_batch``): all centres of a dataset in three kernel
+launches, emitted as one packed ``NeighborhoodBatch`` resident in HBM (this also subsumes ``NetworkxToHetero`` +
+``ToTconvHetero`` + PyG ``collate`` of ``workload.py:265-290`` / ``transforms.py:180-255,319-412``).
+
+No CPU fallback: everything here raises if the CUDA library or a CUDA device is unavailable.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph import TargetCSR, csr_from_networkx
+
+MODE_HETERO = 0
+MODE_CANONICAL = 1
+MODE_KHOP = 2
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("desco_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+@dataclass
+class DeviceCSR:
+    """Target graphs resident in HBM (int32 CSR, see graph.TargetCSR)."""
+
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    graph_ptr: torch.Tensor
+    max_graph_nodes: int
+    host: Optional[TargetCSR] = None
+
+    @property
+    def num_nodes(self) -> int:
+        return self.rowptr.numel() - 1
+
+    @property
+    def num_directed_edges(self) -> int:
+        return self.col.numel()
+
+    @property
+    def num_graphs(self) -> int:
+        return self.graph_ptr.numel() - 1
+
+    @staticmethod
+    def from_host(csr: TargetCSR, device=None, non_blocking: bool = False) -> "DeviceCSR":
+        dev = _require_cuda(device)
+        if csr.rowptr.dtype != np.int32:
+            raise ValueError("target graph exceeds int32 edge offsets")
+
+        def up(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            return t.to(dev, non_blocking=non_blocking)
+
+        mg = int(np.diff(csr.graph_ptr).max()) if csr.num_graphs else 1
+        return DeviceCSR(up(csr.rowptr), up(csr.col), up(csr.graph_ptr), max(mg, 1), csr)
+
+
+@dataclass
+class NeighborhoodBatch:
+    """Packed canonical neighborhoods in HBM.  Row order inside a neighborhood = ascending node id, so the canonical
+    node is the last row (``nbh_ptr[g+1]-1``) and every other row is a "count" node."""
+
+    nbh_ptr: torch.Tensor  # int32 [G+1]
+    node_gid: torch.Tensor  # int32 [V]
+    edge_ptr: torch.Tensor  # int32 [V+1]
+    edge_col: torch.Tensor  # int32 [E]  batch-global row of the other endpoint
+    edge_tri: torch.Tensor  # uint8 [E]  1 = union_triangle, 0 = union_tride
+    centre: torch.Tensor  # int32 [G]
+    indicator: Optional[torch.Tensor] = None  # uint8 [#centres]  == nx_neighs_indicator (workload.py:294)
+    centre_graph: Optional[torch.Tensor] = None  # int32 [#centres]
+    graph_ptr: Optional[torch.Tensor] = None
+    num_neighborhoods: int = 0
+    num_rows: int = 0
+    num_edges: int = 0
+    hetero: bool = True  # False: query graphs / homogeneous neighborhoods (single node type)
+    _cache: dict = field(default_factory=dict, repr=False)
+
+    @property
+    def num_graphs(self) -> int:  # PyG Batch vocabulary: one "graph" per neighborhood
+        return self.num_neighborhoods
+
+    def to_numpy(self) -> Dict[str, np.ndarray]:
+        out = {k: getattr(self, k).cpu().numpy() for k in ("nbh_ptr", "node_gid", "edge_ptr", "edge_col", "edge_tri", "centre")}
+        if self.indicator is not None:
+            out["indicator"] = self.indicator.cpu().numpy().astype(bool)
+        out["index"] = self.index()
+        return out
+
+    def index(self) -> np.ndarray:
+        """``nx_neighs_index``: (graph id, local node id) per kept neighborhood (``workload.py:259,293``)."""
+        c = self.centre.cpu().numpy().astype(np.int64)
+        if self.graph_ptr is None:
+            return np.stack([np.zeros_like(c), c], axis=1)
+        gp = self.graph_ptr.cpu().numpy().astype(np.int64)
+        gid = np.searchsorted(gp, c, side="right") - 1
+        return np.stack([gid, c - gp[gid]], axis=1)
+
+    @staticmethod
+    def from_numpy(d: Dict[str, np.ndarray], device=None, hetero: bool = True) -> "NeighborhoodBatch":
+        dev = _require_cuda(device)
+        t = lambda k, dt: torch.from_numpy(np.ascontiguousarray(d[k]).astype(dt)).to(dev)
+        V = int(d["nbh_ptr"][-1])
+        node_gid = t("node_gid", np.int32) if "node_gid" in d else torch.arange(V, dtype=torch.int32, device=dev)
+        centre = t("centre", np.int32) if "centre" in d else node_gid[(t("nbh_ptr", np.int64)[1:] - 1)]
+        return NeighborhoodBatch(
+            t("nbh_ptr", np.int32), node_gid, t("edge_ptr", np.int32), t("edge_col", np.int32), t("edge_tri", np.uint8),
+            centre, None, None, None, len(d["nbh_ptr"]) - 1, V, int(d["edge_ptr"][-1]), hetero,
+        )
+
+
+def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: int, mode: Union[int, str] = "hetero",
+                    ) -> NeighborhoodBatch:
+    """All canonical neighborhoods of ``centres`` (default: every node, in dataset order) in one packed batch.
+
+    Replaces the double Python loop of ``NeighborhoodDataset.process`` (``workload.py:250-272``)."""
+    lib = _lib.load()
+    dev = graph.rowptr.device
+    if isinstance(mode, str):
+        mode = {"hetero": MODE_HETERO, "canonical": MODE_CANONICAL, "khop": MODE_KHOP}[mode]
+    if centres is None:
+        centres = torch.arange(graph.num_nodes, dtype=torch.int32, device=dev)
+    centres = centres.to(device=dev, dtype=torch.int32).contiguous()
+    C = centres.numel()
+    i32 = dict(dtype=torch.int32, device=dev)
+    scratch = torch.empty((6, max(C, 1)), **i32)  # nv, ne, centre_graph, keep_rank, node_off, edge_off
+    nv, ne, cg, rank, noff, eoff = scratch.unbind(0)
+    nbh_ptr = torch.empty(C + 1, **i32)
+    centre_out = torch.empty(max(C, 1), **i32)
+    indicator = torch.empty(max(C, 1), dtype=torch.uint8, device=dev)
+    small = torch.zeros(4, **i32)  # totals[3] + status
+    totals, status = small[:3], small[3:]
+    with torch.cuda.device(dev):
+        st = _stream()
+        _lib.check(lib.desco_partition_count(
+            _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres), C, depth, mode,
+            graph.max_graph_nodes, _ptr(nv), _ptr(ne), _ptr(cg), _ptr(status), st), "desco_partition_count")
+        wbytes = int(lib.desco_partition_scan_workspace_bytes(C))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.desco_partition_scan(
+            _ptr(centres), _ptr(nv), _ptr(ne), C, _ptr(rank), _ptr(noff), _ptr(eoff), _ptr(nbh_ptr), _ptr(centre_out),
+            _ptr(indicator), _ptr(totals), _ptr(work), wbytes, st), "desco_partition_scan")
+        G, V, E, code = (int(x) for x in small.cpu())  # the one host sync of the partition: output sizes
+        if code != 0:
+            _lib.check(code, "partition kernel (device status)")
+        node_gid = torch.empty(V, **i32)
+        edge_ptr = torch.zeros(V + 1, **i32)
+        edge_col = torch.empty(E, **i32)
+        edge_tri = torch.empty(E, dtype=torch.uint8, device=dev)
+        if V > 0:
+            _lib.check(lib.desco_partition_fill(
+                _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres), C, depth,
+                mode, graph.max_graph_nodes, _ptr(nv), _ptr(ne), _ptr(cg), _ptr(noff), _ptr(eoff), _ptr(node_gid),
+                _ptr(edge_ptr), _ptr(edge_col), _ptr(edge_tri), _ptr(status), st), "desco_partition_fill")
+    return NeighborhoodBatch(
+        nbh_ptr[: G + 1], node_gid, edge_ptr, edge_col, edge_tri, centre_out[:G], indicator[:C], cg[:C],
+        graph.graph_ptr, G, V, E, hetero=(mode == MODE_HETERO),
+    )
+
+
+def shmp_edge_types(edge_ptr: torch.Tensor, edge_col: torch.Tensor) -> torch.Tensor:
+    """Triangle / tride flag of every directed edge of a packed batch (``transforms.py:201-225``)."""
+    lib = _lib.load()
+    _require_cuda(edge_ptr.device)
+    tri = torch.empty(edge_col.numel(), dtype=torch.uint8, device=edge_ptr.device)
+    with torch.cuda.device(edge_ptr.device):
+        _lib.check(lib.desco_shmp_edge_types(_ptr(edge_ptr), _ptr(edge_col), edge_ptr.numel() - 1, _ptr(tri), _stream()),
+                   "desco_shmp_edge_types")
+    return tri
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in single-centre signatures (nx.Graph in, nx.Graph out)
+# ---------------------------------------------------------------------------------------------
+
+
+def _to_nx_graph(graph):
+    import networkx as nx
+
+    if isinstance(graph, nx.Graph):
+        return graph
+    if hasattr(graph, "edge_index") and hasattr(graph, "num_nodes"):  # PyG Data duck type (data.py:358-359,380-381)
+        g = nx.Graph()
+        g.add_nodes_from(range(int(graph.num_nodes)))
+        ei = graph.edge_index.cpu().numpy()
+        g.add_edges_from((int(a), int(b)) for a, b in ei.T if a <= b)
+        return g
+    raise TypeError(f"unsupported graph type {type(graph)}")
+
+
+def _device_graph_for(graph):
+    """nx graph with arbitrary integer node labels -> (DeviceCSR over dense ids that preserve label order, labels)."""
+    labels = sorted(graph.nodes)
+    if labels and (labels[0] != 0 or labels[-1] != len(labels) - 1):
+        import networkx as nx
+
+        dense = nx.relabel_nodes(graph, {u: i for i, u in enumerate(labels)}, copy=True)
+    else:
+        dense = graph
+    return DeviceCSR.from_host(csr_from_networkx([dense])), labels
+
+
+def _neigh_as_nx(graph, labels, batch: NeighborhoodBatch, mark: str):
+    import networkx as nx
+
+    b = batch.to_numpy()
+    out = nx.Graph()
+    if batch.num_neighborhoods == 0:  # edge-free neighborhood: the reference still returns the lone centre
+        return None
+    rows = [labels[int(g)] for g in b["node_gid"]]
+    for u in rows:
+        out.add_node(u, **graph.nodes[u])
+    for r, u in enumerate(rows):
+        for e in range(int(b["edge_ptr"][r]), int(b["edge_ptr"][r + 1])):
+            out.add_edge(u, rows[int(b["edge_col"][e])])
+    return out
+
+
+def _k_hop(graph, start_node, k, mode):
+    graph = _to_nx_graph(graph)
+    dg, labels = _device_graph_for(graph)
+    c = torch.tensor([labels.index(start_node)], dtype=torch.int32, device=dg.rowptr.device)
+    batch = partition_batch(dg, c, k, mode)
+    return graph, labels, batch
+
+
+def get_neigh_hetero(graph, node, radius: int):
+    """Drop-in for ``data.py:375-396``: nx.Graph of the canonical neighborhood, node attr ``type``."""
+    graph, labels, batch = _k_hop(graph, node, radius, MODE_HETERO)
+    neigh = _neigh_as_nx(graph, labels, batch, "type")
+    if neigh is None:
+        import networkx as nx
+
+        neigh = nx.Graph()
+        neigh.add_node(node, **graph.nodes[node])
+    for u in neigh.nodes:
+        neigh.nodes[u]["type"] = "count"
+    neigh.nodes[node]["type"] = "canonical"
+    return neigh
+
+
+def get_neigh_canonical(graph, node, radius: int):
+    """Drop-in for ``data.py:353-372``: restricted-BFS variant, ``node_feature`` = 1 at the centre."""
+    graph, labels, batch = _k_hop(graph, node, radius, MODE_CANONICAL)
+    neigh = _neigh_as_nx(graph, labels, batch, "node_feature")
+    if neigh is None:
+        import networkx as nx
+
+        neigh = nx.Graph()
+        neigh.add_node(node, **graph.nodes[node])
+    for u in neigh.nodes:
+        neigh.nodes[u]["node_feature"] = torch.zeros(1)
+    neigh.nodes[node]["node_feature"] = torch.ones(1)
+    return neigh
+
+
+def k_neigh(G, start_node, k):
+    """Drop-in for ``data.py:329-338`` (node list of the unrestricted k-hop ball)."""
+    graph, labels, batch = _k_hop(G, start_node, k, MODE_KHOP)
+    if batch.num_neighborhoods == 0:
+        return [start_node]
+    return [labels[int(g)] for g in batch.node_gid.cpu().numpy()]
+
+
+def k_neigh_canonical(G, start_node, k):
+    """Drop-in for ``data.py:341-350`` (node list of the restricted k-hop BFS)."""
+    return list(get_neigh_canonical(G, start_node, k).nodes)

@@ -68,10 +68,20 @@ def _key(et: Tuple[str, str, str]) -> str:
 # ---------------------------------------------------------------------------------------------
 
 
-def hetero_views(batch: Dict[str, np.ndarray], hetero: bool = True):
+def hetero_views(batch: Dict[str, np.ndarray], hetero: bool = True, pyg_batch_size: Optional[int] = None,
+                 self_loop_quirk: bool = True):
     """Per node type: row ids into the packed row space + graph id per row.  Per relation: edge_index in per-type
     local ids (``transforms.py:342-367`` id assignment + ``:227-253`` type split).  ``hetero=False`` = query graphs:
-    one node type ``union_node`` (``transforms.py:343-345``)."""
+    one node type ``union_node`` (``transforms.py:343-345``).
+
+    REFERENCE QUIRK reproduced when ``self_loop_quirk``: ``SAGEConv.forward`` calls ``remove_self_loops`` on EVERY
+    relation (``gnn_model.py:389-390``), including the bipartite count<->canonical ones whose two rows live in
+    different id spaces, so an edge whose per-type local source id equals its per-type local destination id is
+    silently dropped from message passing.  Ids are local to one collated PyG batch (``pyg_batch_size`` consecutive
+    neighborhoods, ``config.py:255`` default 512; None = the whole input is one batch).  In the packed layout this
+    hits neighborhood g of a batch exactly when every earlier neighborhood of that batch has 2 rows and the canonical
+    node is adjacent to its lowest-id count node.  (Found by running the reference's own SAGEConv, see
+    tests/golden/make_golden.py.)"""
     nbh_ptr = torch.as_tensor(batch["nbh_ptr"], dtype=torch.long)
     edge_ptr = torch.as_tensor(batch["edge_ptr"], dtype=torch.long)
     col = torch.as_tensor(batch["edge_col"], dtype=torch.long)
@@ -94,10 +104,23 @@ def hetero_views(batch: Dict[str, np.ndarray], hetero: bool = True):
         rows[t] = torch.nonzero(m).flatten()
         local[rows[t]] = torch.arange(len(rows[t]))
         batch_vec[t] = graph_of_row[rows[t]]
+    # per-type local id inside its own collated PyG batch (chunks of pyg_batch_size neighborhoods)
+    bs = G if not pyg_batch_size else int(pyg_batch_size)
+    chunk_of_row = graph_of_row // max(bs, 1)
+    chunk_local = torch.zeros(V, dtype=torch.long)
+    for t, m in type_of.items():
+        r = rows[t]
+        ch = chunk_of_row[r]
+        first = torch.zeros(int(ch.max()) + 1 if len(ch) else 1, dtype=torch.long)
+        if len(ch):
+            first.scatter_reduce_(0, ch, torch.arange(len(r)), reduce="amin", include_self=False)
+            chunk_local[r] = torch.arange(len(r)) - first[ch]
     edges = {}
     for (s, r, d) in meta[1]:
         want_tri = r.endswith("triangle")
         m = type_of[s][src] & type_of[d][dst] & (tri == want_tri)
+        if self_loop_quirk and s != d:
+            m = m & (chunk_local[src] != chunk_local[dst])  # remove_self_loops on a bipartite edge_index
         edges[(s, r, d)] = torch.stack([local[src[m]], local[dst[m]]])
     return SimpleNamespace(rows=rows, batch=batch_vec, edges=edges, num_graphs=G, meta=meta)
 
@@ -128,12 +151,11 @@ class HeteroSAGECore(nn.Module):
         self.meta = meta
         self.layer_num = args.layer_num
         self.pre_mp = nn.ModuleList([nn.ModuleDict({t: nn.Linear(input_dim, hidden_dim) for t in meta[0]})])
-        self.convs = nn.ModuleList(
-            [nn.ModuleDict({_key(et): SAGEConv(hidden_dim, hidden_dim) for et in meta[1]}) for _ in range(args.layer_num)]
-        )
-        self.updates = nn.ModuleList(
-            [nn.ModuleDict({t: nn.Linear(2 * hidden_dim, hidden_dim) for t in meta[0]}) for _ in range(args.layer_num)]
-        )
+        self.convs = nn.ModuleList()
+        self.updates = nn.ModuleList()
+        for _ in range(args.layer_num):  # conv then update per layer: the reference's construction (= RNG) order, :146-190
+            self.convs.append(nn.ModuleDict({_key(et): SAGEConv(hidden_dim, hidden_dim) for et in meta[1]}))
+            self.updates.append(nn.ModuleDict({t: nn.Linear(2 * hidden_dim, hidden_dim) for t in meta[0]}))
         self.post_input_dim = hidden_dim * args.layer_num + hidden_dim
 
     def forward(self, x_dict, edge_index_dict):
@@ -201,19 +223,19 @@ class NeighborhoodCountingModel(nn.Module):
     def get_query_emb(self, query_batch):
         return self.emb_model_query(hetero_views(query_batch, hetero=False))  # :311-316
 
-    def graph_to_embed(self, batch):
-        return self.emb_model(hetero_views(batch, hetero=True))
+    def graph_to_embed(self, batch, pyg_batch_size=None, self_loop_quirk=True):
+        return self.emb_model(hetero_views(batch, True, pyg_batch_size, self_loop_quirk))
 
-    def pre_exponent(self, batch, query_batch):
+    def pre_exponent(self, batch, query_batch, pyg_batch_size=None, self_loop_quirk=True):
         emb_q = self.get_query_emb(query_batch)
-        emb_t = self.graph_to_embed(batch)
+        emb_t = self.graph_to_embed(batch, pyg_batch_size, self_loop_quirk)
         out = []
         for q in emb_q:  # lightning_model.py:212-219
             out.append(self.count_model(torch.cat((emb_t, q.expand_as(emb_t)), dim=-1)))
         return torch.cat(out, dim=-1)
 
-    def graph_to_count(self, batch, query_batch):
-        return 2 ** self.pre_exponent(batch, query_batch) - 1  # :221
+    def graph_to_count(self, batch, query_batch, pyg_batch_size=None, self_loop_quirk=True):
+        return 2 ** self.pre_exponent(batch, query_batch, pyg_batch_size, self_loop_quirk) - 1  # :221
 
 
 # ---------------------------------------------------------------------------------------------

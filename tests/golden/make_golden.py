@@ -138,7 +138,8 @@ def main():
                 s, _, d = et
                 conv = ref.SAGEConv(64, 64)
                 conv.lin.load_state_dict(core.convs[l]["__".join(et)].lin.state_dict())
-                xin = x[s] if s == d else (x[s], x[d])  # App. B.2
+                xin = x[s] if s == d else (x[s], x[d])  # App. B.2; SAGEConv.forward then runs remove_self_loops
+                # on this bipartite edge_index too (gnn_model.py:389-390) - the quirk oracle/model.py documents
                 outs[d].append(conv(xin, views.edges[et]))
             nx_ = {}
             for t in views.meta[0]:
@@ -154,7 +155,7 @@ def main():
         return base.post_mp(ref_shim.global_add_pool(cat, bv, views.num_graphs))
 
     with torch.no_grad():
-        t_emb = ref_leaf_forward(om.emb_model, M.hetero_views(b, True))
+        t_emb = ref_leaf_forward(om.emb_model, M.hetero_views(b, True, self_loop_quirk=False))  # the reference SAGEConv drops them itself
         q_emb = ref_leaf_forward(om.emb_model_query, M.hetero_views(qb, False))
         pred = torch.cat([om.count_model(torch.cat((t_emb, q.expand_as(t_emb)), -1)) for q in q_emb], -1)
         count = 2 ** pred - 1

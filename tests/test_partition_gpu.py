@@ -1,0 +1,122 @@
+"""GPU parity: canonical partition + SHMP typing kernels (through the C ABI) vs the oracle and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from desco_b200.graph import (TargetCSR, csr_from_networkx, first_nonempty_centres, gen_cox2_shaped,
+                              gen_enzymes_shaped, gen_imdb_shaped, gen_mutag_shaped, gen_syn1827_shaped)
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("nbh_ptr", "node_gid", "edge_ptr", "edge_col", "edge_tri", "centre", "index", "indicator")
+
+
+def _gpu_partition(csr, depth, mode, centres=None):
+    from desco_b200.data import DeviceCSR, partition_batch
+
+    d = DeviceCSR.from_host(csr)
+    c = None if centres is None else torch.as_tensor(centres, dtype=torch.int32, device=d.rowptr.device)
+    return partition_batch(d, c, depth, mode).to_numpy()
+
+
+@pytest.mark.parametrize("name", ["kat", "mutag24", "enzymes12", "imdb6"])
+@pytest.mark.parametrize("mode", ["hetero", "canonical"])
+def test_partition_matches_reference_golden(cuda_device, golden_dir, name, mode):
+    z = np.load(os.path.join(golden_dir, f"partition_{name}.npz"))
+    csr = TargetCSR(z["rowptr"], z["col"], z["graph_ptr"])
+    for depth in (1, 2, 3, 4):
+        b = _gpu_partition(csr, depth, mode)
+        for k in KEYS:
+            assert np.array_equal(b[k], z[f"{mode}_d{depth}_{k}"]), (name, mode, depth, k)
+
+
+@pytest.mark.parametrize("gen,kw", [(gen_mutag_shaped, {}), (gen_cox2_shaped, dict(num_graphs=60)),
+                                    (gen_enzymes_shaped, dict(num_graphs=80)), (gen_imdb_shaped, dict(num_graphs=40)),
+                                    (gen_syn1827_shaped, dict(stride=160))])
+def test_partition_matches_oracle_on_config_shapes(cuda_device, gen, kw):
+    from oracle import partition as P
+
+    csr = gen(seed=0, **kw)
+    ref = P.partition_dataset(csr, 4, mode="hetero")
+    b = _gpu_partition(csr, 4, "hetero")
+    for k in KEYS:
+        assert np.array_equal(b[k], ref[k]), (gen.__name__, k)
+
+
+def test_partition_cta_regime_large_graph(cuda_device):
+    """A single graph above 2048 nodes takes the CTA-per-centre kernel; compare a centre sample with the oracle."""
+    from oracle import partition as P
+
+    from desco_b200.graph import gen_powerlaw
+
+    csr = gen_powerlaw(6000, 24000, seed=1)
+    rng = np.random.default_rng(0)
+    centres = np.sort(rng.choice(csr.num_nodes, size=96, replace=False)).astype(np.int32)
+    for depth in (2, 3):
+        ref = P.partition_dataset(csr, depth, mode="hetero", centres=centres)
+        b = _gpu_partition(csr, depth, "hetero", centres)
+        for k in KEYS:
+            assert np.array_equal(b[k], ref[k]), (depth, k)
+
+
+def test_partition_edge_cases(cuda_device):
+    import networkx as nx
+
+    # isolated node, single edge, star, empty centre list, depth 0
+    g = nx.Graph()
+    g.add_nodes_from(range(6))
+    g.add_edges_from([(1, 2), (3, 4), (3, 5)])
+    csr = csr_from_networkx([g, nx.path_graph(3)])
+    b = _gpu_partition(csr, 4, "hetero")
+    assert b["indicator"].tolist() == [False, False, True, False, True, True, False, True, True]
+    b0 = _gpu_partition(csr, 0, "hetero")
+    assert b0["indicator"].sum() == 0 and b0["nbh_ptr"].tolist() == [0]
+    be = _gpu_partition(csr, 4, "hetero", centres=np.zeros(0, dtype=np.int32))
+    assert be["nbh_ptr"].tolist() == [0] and len(be["edge_col"]) == 0
+
+
+def test_partition_properties_full_size(cuda_device):
+    """Config-2 size (whole ENZYMES-shaped pool): size-independent invariants."""
+    csr = gen_enzymes_shaped(seed=0)
+    b = _gpu_partition(csr, 4, "hetero")
+    assert np.array_equal(np.nonzero(b["indicator"])[0][:4096], first_nonempty_centres(csr, 4096))
+    assert np.array_equal(b["node_gid"][b["nbh_ptr"][1:] - 1], b["centre"])  # canonical = last row = max id
+    V = int(b["nbh_ptr"][-1])
+    dst = np.repeat(np.arange(V, dtype=np.int64), np.diff(b["edge_ptr"]))
+    key = dst * V + b["edge_col"]
+    rev = b["edge_col"].astype(np.int64) * V + dst
+    order, rorder = np.argsort(key), np.argsort(rev)
+    assert np.array_equal(key[order], rev[rorder])  # symmetric edge set
+    assert np.array_equal(b["edge_tri"][order], b["edge_tri"][rorder])  # symmetric types
+    nb = np.repeat(np.arange(len(b["centre"])), np.diff(b["nbh_ptr"]))
+    assert np.array_equal(nb[dst], nb[b["edge_col"]])  # edges never leave their neighborhood
+    assert (b["node_gid"][dst] != b["node_gid"][b["edge_col"]]).all()
+
+
+def test_standalone_edge_typing(cuda_device):
+    from desco_b200.data import shmp_edge_types
+    from oracle import partition as P
+
+    csr = gen_imdb_shaped(seed=2, num_graphs=20)
+    ref = P.partition_dataset(csr, 4)
+    tri = shmp_edge_types(torch.as_tensor(ref["edge_ptr"], device="cuda"), torch.as_tensor(ref["edge_col"], device="cuda"))
+    assert np.array_equal(tri.cpu().numpy(), ref["edge_tri"])
+
+
+def test_drop_in_single_centre_api(cuda_device):
+    import networkx as nx
+
+    from desco_b200 import data as D
+    from oracle import partition as P
+
+    G4 = nx.Graph([(9, 10), (10, 0), (9, 1), (1, 2), (2, 3), (3, 4), (4, 0)])
+    for k in (2, 3, 5):
+        a, b = D.get_neigh_hetero(G4, 9, k), P.get_neigh_hetero(G4, 9, k)
+        assert sorted(a.nodes) == sorted(b.nodes) and {frozenset(e) for e in a.edges} == {frozenset(e) for e in b.edges}
+        assert a.nodes[9]["type"] == "canonical" and all(a.nodes[u]["type"] == "count" for u in a.nodes if u != 9)
+        a, b = D.get_neigh_canonical(G4, 9, k), P.get_neigh_canonical(G4, 9, k)
+        assert sorted(a.nodes) == sorted(b.nodes)
+        assert sorted(D.k_neigh(G4, 9, k)) == sorted(P.k_neigh(G4, 9, k))
+    assert sorted(D.get_neigh_hetero(G4, 0, 4).nodes) == [0]
