@@ -380,9 +380,10 @@ int launch_partition(const int32_t* rowptr, const int32_t* col, const int32_t* g
                      int32_t* ne, int32_t* centre_graph, int fill, const int32_t* node_off, const int32_t* edge_off,
                      int32_t* node_gid, int32_t* edge_ptr, int32_t* edge_col, uint8_t* edge_tri, int32_t* status,
                      cudaStream_t stream) {
-  if (!rowptr || !col || !graph_ptr || !centres || !nv || !ne || !centre_graph || !status) return DESCO_EINVAL;
-  if (depth < 0 || mode < DESCO_MODE_HETERO || mode > DESCO_MODE_KHOP || max_graph_nodes <= 0) return DESCO_EINVAL;
+  if (depth < 0 || mode < DESCO_MODE_HETERO || mode > DESCO_MODE_KHOP || max_graph_nodes <= 0 || num_centres < 0)
+    return DESCO_EINVAL;
   if (num_centres == 0) return DESCO_OK;
+  if (!rowptr || !col || !graph_ptr || !centres || !nv || !ne || !centre_graph || !status) return DESCO_EINVAL;
   const int max_words = (max_graph_nodes + 31) / 32;
   const int sms = desco_num_sms();
   if (max_words <= 64) {  // warp per centre
@@ -436,9 +437,10 @@ int desco_partition_scan(const int32_t* centres, const int32_t* nv, const int32_
                          int32_t* keep_rank, int32_t* node_off, int32_t* edge_off, int32_t* nbh_ptr,
                          int32_t* centre_out, uint8_t* indicator, int32_t* totals, void* workspace,
                          int64_t workspace_bytes, void* stream) {
-  if (!centres || !nv || !ne || !keep_rank || !node_off || !edge_off || !nbh_ptr || !centre_out || !totals || !workspace)
-    return DESCO_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
+  if (!nbh_ptr || !totals || num_centres < 0) return DESCO_EINVAL;
+  if (num_centres > 0 && (!centres || !nv || !ne || !keep_rank || !node_off || !edge_off || !centre_out || !workspace))
+    return DESCO_EINVAL;
   if (num_centres == 0) {
     DESCO_CUDA_TRY(cudaMemsetAsync(totals, 0, 3 * sizeof(int32_t), s));
     DESCO_CUDA_TRY(cudaMemsetAsync(nbh_ptr, 0, sizeof(int32_t), s));

@@ -1,0 +1,193 @@
+"""GNN modules of the DeSCo hot path - host side of csrc/shmp.cu and csrc/gossip.cu.
+
+Mirrors ``subgraph_counting/gnn_model.py`` (reference @ 4508f7a): ``BaseGNN`` :18, ``BaseGNNCore`` :115, ``SAGEConv`` :362,
+``GossipConv`` :280.  The modules own ``torch.nn`` parameters under the reference's state-dict key names (after
+``to_hetero_old``: ``gnn_core.pre_mp.0.<type>``, ``gnn_core.convs.<l>.<src>__<rel>__<dst>.lin``,
+``gnn_core.updates.<l>.<type>``, ``anchor_mlp.0``, ``post_mp.{0,3,5,7}``) so reference checkpoints
+load unchanged; ``forward`` packs them into the fused K-major blobs include/desco_b200.h documents and runs the CUDA
+kernels.  There is no eager/CPU forward: without the CUDA library these modules raise.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .data import NeighborhoodBatch, _ptr, _stream
+
+TARGET_META = (
+    ["count", "canonical"],
+    [
+        ("count", "union_triangle", "count"),
+        ("count", "union_tride", "count"),
+        ("count", "union_triangle", "canonical"),
+        ("count", "union_tride", "canonical"),
+        ("canonical", "union_triangle", "count"),
+        ("canonical", "union_tride", "count"),
+    ],
+)  # lightning_model.py:376-385
+QUERY_META = (
+    ["union_node"],
+    [("union_node", "union_triangle", "union_node"), ("union_node", "union_tride", "union_node")],
+)  # lightning_model.py:404-413
+
+PRECISION = {"fp32": 0, "tf32x3": 1, "bf16": 2}
+
+
+def _key(et) -> str:
+    return "__".join(et)
+
+
+def _params_version(module: nn.Module) -> Tuple:
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+class SAGEConv(nn.Module):
+    """``gnn_model.py:362-404``: ``lin(sum_{j->i} x_j)``.  Parameter holder; the arithmetic runs fused inside
+    ``BaseGNN.forward`` (csrc/shmp.cu), one launch per layer for all relations."""
+
+    def __init__(self, in_channels, out_channels, aggr="add", **kwargs):
+        super().__init__()
+        assert aggr == "add"
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = nn.Linear(in_channels, out_channels)
+
+    def reset_parameters(self):
+        self.lin.reset_parameters()
+
+    def __repr__(self):
+        return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)
+
+
+class BaseGNNCore(nn.Module):
+    """``gnn_model.py:115-277`` in its ``to_hetero`` form (node-level modules per node type, convs per edge type).
+    Only the default SHMP configuration is a CUDA path: conv_type SAGE, hidden 64 (``config.py:247-264``)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, args, meta=TARGET_META, **kwargs):
+        super().__init__()
+        if args.conv_type != "SAGE":
+            raise NotImplementedError("only the default SAGE SHMP core is built (GIN/GCN/GAT/PNA are ablations)")
+        if hidden_dim != 64:
+            raise NotImplementedError("the sm_100a kernels are specialised for hidden_dim = 64 (config.py:250)")
+        self.meta = meta
+        self.layer_num = args.layer_num
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
+        self.dropout = args.dropout
+        self.pre_mp = nn.ModuleList([nn.ModuleDict({t: nn.Linear(input_dim, hidden_dim) for t in meta[0]})])
+        self.convs = nn.ModuleList()
+        self.updates = nn.ModuleList()
+        for _ in range(args.layer_num):  # conv then update per layer: the reference's construction order (:146-190)
+            self.convs.append(nn.ModuleDict({_key(et): SAGEConv(hidden_dim, hidden_dim) for et in meta[1]}))
+            self.updates.append(nn.ModuleDict({t: nn.Linear(2 * hidden_dim, hidden_dim) for t in meta[0]}))
+        self.post_input_dim = hidden_dim * args.layer_num + hidden_dim
+
+
+def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
+    """Fuse + transpose the parameters into the blobs of include/desco_b200.h (fp64 on the host, rounded once)."""
+    core = base.gnn_core
+    hetero = "canonical" in core.meta[0]
+    types = core.meta[0]
+    F = core.hidden_dim
+    dev = base.post_mp[0].weight.device
+    d = lambda t: t.detach().to("cpu", torch.float64)
+    pre = []
+    for t in types:
+        lin = core.pre_mp[0][t]
+        pre += [d(lin.weight).t().contiguous().flatten(), d(lin.bias)]
+    layers = []
+    for l in range(core.layer_num):
+        def fused(dst, rels):
+            U, u = d(core.updates[l][dst].weight), d(core.updates[l][dst].bias)
+            Um, Uh = U[:, :F], U[:, F:]
+            blocks = [(Um @ d(core.convs[l][_key(r)].lin.weight)).t() for r in rels]
+            return blocks, Um, Uh, u
+
+        if hetero:
+            cc = [("count", "union_triangle", "count"), ("count", "union_tride", "count")]
+            ac = [("canonical", "union_triangle", "count"), ("canonical", "union_tride", "count")]
+            ca = [("count", "union_triangle", "canonical"), ("count", "union_tride", "canonical")]
+            blocks, Um, Uh, u = fused("count", cc)
+            Wc = torch.cat(blocks + [Uh.t()], 0)
+            bsum = sum(d(core.convs[l][_key(r)].lin.bias) for r in cc + ac)
+            bias_c = Um @ bsum + u
+            Cw = torch.cat([(Um @ d(core.convs[l][_key(r)].lin.weight)).t() for r in ac], 1)  # [F][2F]
+            blocks_a, Uma, Uha, ua = fused("canonical", ca)
+            Wa = torch.cat(blocks_a + [Uha.t()], 0)
+            bias_a = Uma @ sum(d(core.convs[l][_key(r)].lin.bias) for r in ca) + ua
+        else:
+            uu = [("union_node", "union_triangle", "union_node"), ("union_node", "union_tride", "union_node")]
+            blocks, Um, Uh, u = fused("union_node", uu)
+            Wc = torch.cat(blocks + [Uh.t()], 0)
+            bias_c = Um @ sum(d(core.convs[l][_key(r)].lin.bias) for r in uu) + u
+            Cw = torch.zeros(F, 2 * F, dtype=torch.float64)
+            Wa = torch.zeros(3 * F, F, dtype=torch.float64)
+            bias_a = torch.zeros(F, dtype=torch.float64)
+        layers += [Wc.contiguous().flatten(), bias_c, Cw.contiguous().flatten(), Wa.contiguous().flatten(), bias_a]
+    ro = [d(base.anchor_mlp[0].weight).t().contiguous().flatten(), d(base.anchor_mlp[0].bias)]
+    for i in (0, 3, 5, 7):
+        ro += [d(base.post_mp[i].weight).t().contiguous().flatten(), d(base.post_mp[i].bias)]
+    f32 = lambda parts: torch.cat(parts).to(torch.float32).to(dev).contiguous()
+    return {"pre": f32(pre), "layers": f32(layers), "readout": f32(ro)}
+
+
+class BaseGNN(nn.Module):
+    """``gnn_model.py:18-109`` (SHMP path): ``forward(batch) -> [num_neighborhoods, output_dim]``."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, args, meta=TARGET_META, **kwargs):
+        super().__init__()
+        if output_dim != hidden_dim:
+            raise NotImplementedError("post_mp output width is fixed to hidden_dim on the CUDA path")
+        self.args, self.kwargs = args, kwargs
+        self.dropout, self.layer_num, self.conv_type = args.dropout, args.layer_num, args.conv_type
+        self.use_hetero = getattr(args, "use_hetero", True)
+        self.gnn_core = BaseGNNCore(input_dim, hidden_dim, output_dim, args, meta, **kwargs)
+        p = self.gnn_core.post_input_dim
+        self.anchor_mlp = nn.Sequential(nn.Linear(p, p), nn.LeakyReLU(0.1))
+        self.post_mp = nn.Sequential(
+            nn.Linear(p, hidden_dim), nn.Dropout(args.dropout), nn.LeakyReLU(0.1), nn.Linear(hidden_dim, hidden_dim),
+            nn.ReLU(), nn.Linear(hidden_dim, 256), nn.ReLU(), nn.Linear(256, output_dim),
+        )
+        self.precision = "fp32"
+        self.pyg_batch_size = 0  # 0: the whole NeighborhoodBatch is one collated PyG batch
+        self._packed = None
+        self._packed_version = None
+
+    def packed_weights(self) -> Dict[str, torch.Tensor]:
+        v = _params_version(self)
+        if self._packed is None or v != self._packed_version:
+            self._packed, self._packed_version = pack_shmp_weights(self), v
+        return self._packed
+
+    def forward(self, data: NeighborhoodBatch, query_emb=None, feat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not isinstance(data, NeighborhoodBatch):
+            from .transforms import as_neighborhood_batch
+
+            data = as_neighborhood_batch(data)
+        lib = _lib.load()
+        core = self.gnn_core
+        hetero = "canonical" in core.meta[0]
+        if hetero != data.hetero:
+            raise ValueError("batch node-type layout does not match the model metadata (count/canonical vs union_node)")
+        if self.training and core.dropout > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not a CUDA path (config.py:252 default is 0)")
+        w = self.packed_weights()
+        dev = w["pre"].device
+        G, V = data.num_neighborhoods, data.num_rows
+        out = torch.empty((G, core.hidden_dim), dtype=torch.float32, device=dev)
+        if G == 0:
+            return out
+        wbytes = int(lib.desco_shmp_workspace_bytes(V, G, core.layer_num))
+        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        if feat is not None:
+            feat = feat.to(device=dev, dtype=torch.float32).contiguous()
+            assert feat.shape == (V, core.input_dim)
+        with torch.cuda.device(dev):
+            _lib.check(lib.desco_shmp_forward(
+                _ptr(data.nbh_ptr), _ptr(data.edge_ptr), _ptr(data.edge_col), _ptr(data.edge_tri), G, V, int(hetero),
+                int(self.pyg_batch_size), _ptr(feat), core.input_dim, _ptr(w["pre"]), _ptr(w["layers"]),
+                _ptr(w["readout"]), core.layer_num, core.hidden_dim, _ptr(out), _ptr(work), wbytes,
+                PRECISION[self.precision], _stream()), "desco_shmp_forward")
+        return out

@@ -1,0 +1,173 @@
+"""Model entry points of the DeSCo hot path.
+
+Mirrors ``subgraph_counting/lightning_model.py`` (reference @ 4508f7a): ``gen_queries`` :37,
+``NeighborhoodCountingModel`` :90 (``graph_to_count`` :198, ``graph_to_embed`` :224, ``embed_to_count`` :176,
+``set_queries`` :291, ``get_query_emb`` :311, ``to_hetero_old`` :371, ``predict_step`` :195) and ``GossipCountingModel``
+:535 (``graph_to_count`` :613, ``set_query_emb`` :637, ``_gate_value`` :640).  pytorch_lightning is optional: the
+classes are ``torch.nn.Module`` and expose the Lightning hook names the reference's ``main.py`` calls.
+"""
+from __future__ import annotations
+
+import warnings
+from types import SimpleNamespace
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .data import NeighborhoodBatch, _ptr, _stream, shmp_edge_types
+from .gnn_model import QUERY_META, TARGET_META, BaseGNN
+
+STANDARD_QUERY_IDS = [6, 7, 13, 14, 15, 16, 17, 18, 29, 30, 31, 34, 35, 36, 37, 38, 40, 41, 42, 43, 44, 45, 46, 47,
+                      48, 49, 50, 51, 52]  # gen_query_ids([3,4,5]), data.py:37-58
+
+
+def default_neighborhood_args(**kw) -> SimpleNamespace:
+    """``config.py:247-264``."""
+    d = dict(conv_type="SAGE", layer_num=8, hidden_dim=64, input_dim=1, dropout=0.0, use_hetero=True, use_tconv=True,
+             depth=4, lr=1e-4, weight_decay=0.0, batch_size=512, use_canonical=True)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+def gen_queries(query_ids: Optional[List[int]], queries=None, transform=None, node_feat_len: int = 1, hetero=True,
+                device="cuda"):
+    """``lightning_model.py:37-87``: atlas ids / nx graphs -> (packed query batch, nx graphs).  The SHMP transform
+    (``ToTconvHetero`` on every query, :84-85) is applied on the GPU by the same typing kernel as the targets."""
+    import networkx as nx
+
+    queries_nx = [nx.graph_atlas(i) for i in query_ids] if queries is None else list(queries)
+    nbh_ptr, edge_ptr, edge_col = [0], [0], []
+    for g in queries_nx:
+        nodes = sorted(g.nodes)
+        row0 = nbh_ptr[-1]
+        pos = {u: row0 + i for i, u in enumerate(nodes)}
+        for u in nodes:
+            edge_col.extend(sorted(pos[v] for v in g.neighbors(u) if v != u))
+            edge_ptr.append(len(edge_col))
+        nbh_ptr.append(row0 + len(nodes))
+    dev = torch.device(device)
+    t = lambda a: torch.tensor(a, dtype=torch.int32, device=dev)
+    ep, ec = t(edge_ptr), t(edge_col)
+    tri = shmp_edge_types(ep, ec) if transform is not False else torch.zeros(len(edge_col), dtype=torch.uint8, device=dev)
+    V = nbh_ptr[-1]
+    batch = NeighborhoodBatch(t(nbh_ptr), torch.arange(V, dtype=torch.int32, device=dev), ep, ec, tri,
+                              t(nbh_ptr[1:]) - 1, None, None, None, len(queries_nx), V, len(edge_col), hetero=False)
+    return batch, queries_nx
+
+
+def pack_head_weights(count_model: nn.Sequential, hidden: int) -> torch.Tensor:
+    W1 = count_model[0].weight.detach().to("cpu", torch.float64)  # [4h, 2h]
+    parts = [W1[:, :hidden].t().contiguous().flatten(), W1[:, hidden:].t().contiguous().flatten(),
+             count_model[0].bias.detach().to("cpu", torch.float64), count_model[2].weight.detach().to("cpu", torch.float64).flatten(),
+             count_model[2].bias.detach().to("cpu", torch.float64)]
+    return torch.cat(parts).to(torch.float32).to(count_model[0].weight.device).contiguous()
+
+
+class NeighborhoodCountingModel(nn.Module):
+    def __init__(self, input_dim=1, hidden_dim=64, args=None, **kwargs):
+        super().__init__()
+        args = args or default_neighborhood_args(hidden_dim=hidden_dim, input_dim=input_dim)
+        self.hidden_dim, self.input_dim = hidden_dim, input_dim
+        self.args, self.kwargs = args, kwargs
+        for k, v in vars(args).items():  # lightning_model.py:113-114
+            if not hasattr(self, k):
+                setattr(self, k, v)
+        self.query_loader = None  # the reference holds a DataLoader of query graphs; here: one packed batch
+        self.emb_model = BaseGNN(input_dim, hidden_dim, hidden_dim, args, TARGET_META, emb_channels=hidden_dim, **kwargs)
+        self.emb_model_query = BaseGNN(input_dim, hidden_dim, hidden_dim, args, QUERY_META, emb_channels=hidden_dim, **kwargs)
+        self.count_model = nn.Sequential(nn.Linear(2 * hidden_dim, 4 * hidden_dim), nn.LeakyReLU(), nn.Linear(4 * hidden_dim, 1))
+        self._head = None
+        self._head_version = None
+        self._query_emb_cache = None
+
+    # ---- the reference converts with pyg.nn.to_hetero at run time; these modules are built hetero ----
+    def to_hetero_old(self, tconv_target=False, tconv_query=False):
+        if not (tconv_target and tconv_query):
+            raise NotImplementedError("only the default SHMP (use_tconv=True) metadata is a CUDA path")
+        return self
+
+    def to_hetero(self, order: int = 3, SHMP_target=False, SHMP_query=False):
+        if order != 3:
+            raise NotImplementedError("order-4 (11 relation) SHMP is not built")
+        return self.to_hetero_old(SHMP_target, SHMP_query)
+
+    def on_load_checkpoint(self, checkpoint) -> None:
+        a = checkpoint["hyper_parameters"]["args"]
+        if not (a.use_hetero and a.use_tconv and getattr(a, "use_canonical", True)):
+            raise NotImplementedError("checkpoint was trained without hetero/tconv/canonical: not a CUDA path")
+
+    # ---- precision / batching knobs ----
+    def set_precision(self, precision: str):
+        self.emb_model.precision = precision
+        self.emb_model_query.precision = "fp32"
+        return self
+
+    def set_pyg_batch_size(self, n: int):
+        """Size of the collated batches the reference would form (``config.py:255``); only affects which bipartite
+        edges SAGEConv's remove_self_loops drops (see gnn_model / DESIGN.md)."""
+        self.emb_model.pyg_batch_size = int(n)
+        return self
+
+    # ---- queries ----
+    def set_queries(self, query_ids, queries=None, transform=None, hetero=True, device=None):
+        import networkx as nx
+
+        dev = device if device is not None else self.count_model[0].weight.device
+        batch, queries_nx = gen_queries(query_ids, queries, transform, self.input_dim, hetero, dev)
+        min_len = max(nx.diameter(q) for q in queries_nx)
+        if getattr(self, "depth", 4) < min_len:  # lightning_model.py:302-308
+            warnings.warn("neighborhood diameter {:d} is too small for the queries, the minimum is {:d}".format(self.depth, min_len))
+        self.query_loader = batch
+        self._query_emb_cache = None
+
+    def get_query_emb(self) -> torch.Tensor:
+        if self.query_loader is None:
+            raise RuntimeError("call set_queries first")
+        v = tuple((p.data_ptr(), p._version) for p in self.emb_model_query.parameters())
+        if self._query_emb_cache is None or self._query_emb_cache[0] != v:
+            self._query_emb_cache = (v, self.emb_model_query(self.query_loader))
+        return self._query_emb_cache[1]
+
+    # ---- forward ----
+    def graph_to_embed(self, batch) -> torch.Tensor:
+        return self.emb_model(batch)
+
+    def _head_weights(self):
+        v = tuple((p.data_ptr(), p._version) for p in self.count_model.parameters())
+        if self._head is None or v != self._head_version:
+            self._head, self._head_version = pack_head_weights(self.count_model, self.hidden_dim), v
+        return self._head
+
+    def embed_to_count(self, embs, want_pred=False):
+        """``lightning_model.py:176-193`` for ALL queries at once: embs = (emb_targets [G,h], emb_queries [Q,h])."""
+        lib = _lib.load()
+        emb_t, emb_q = embs
+        emb_t, emb_q = emb_t.contiguous(), emb_q.contiguous()
+        G, Q = emb_t.shape[0], emb_q.shape[0]
+        dev = emb_t.device
+        out = torch.empty((2 if want_pred else 1, G, Q), dtype=torch.float32, device=dev)
+        wb = int(lib.desco_count_head_workspace_bytes(G, Q))
+        work = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
+        w = self._head_weights()
+        with torch.cuda.device(dev):
+            _lib.check(lib.desco_count_head(_ptr(emb_t), G, _ptr(emb_q), Q, _ptr(w), self.hidden_dim,
+                                            _ptr(out[1]) if want_pred else 0, _ptr(out[0]), _ptr(work), wb, _stream()),
+                       "desco_count_head")
+        return (out[0], out[1]) if want_pred else out[0]
+
+    def graph_to_count(self, batch) -> torch.Tensor:
+        """``lightning_model.py:198-222``: [num_neighborhoods, num_queries] = 2**pred - 1."""
+        return self.embed_to_count((self.emb_model(batch), self.get_query_emb()))
+
+    def graph_to_pred(self, batch) -> torch.Tensor:
+        """Pre-exponent of graph_to_count (the quantity the training loss sees, :249)."""
+        return self.embed_to_count((self.emb_model(batch), self.get_query_emb()), want_pred=True)[1]
+
+    def predict_step(self, batch, batch_idx=0) -> torch.Tensor:
+        return self.graph_to_count(batch)
+
+    def forward(self, batch):
+        return self.graph_to_count(batch)

@@ -21,8 +21,7 @@ extern "C" {
 
 #define DESCO_MODE_HETERO 0    /* get_neigh_hetero    subgraph_counting/data.py:375-396 (default, hetero_graph=True)  */
 #define DESCO_MODE_CANONICAL 1 /* get_neigh_canonical subgraph_counting/data.py:353-372 (hetero_graph=False)          */
-
-#define DESCO_MODE_KHOP 2      /* k_neigh             subgraph_counting/data.py:329-338 (plain k-hop ball, no filter)      */
+#define DESCO_MODE_KHOP 2      /* k_neigh             subgraph_counting/data.py:329-338 (plain k-hop ball, no filter) */
 
 #define DESCO_PRECISION_FP32 0 /* fp32 FFMA everywhere: the 1e-4 parity path                                           */
 #define DESCO_PRECISION_TF32X3 1 /* tcgen05 kind::tf32, 3-pass hi/lo split: fp32-level error on the tensor pipe        */
@@ -76,6 +75,47 @@ int desco_partition_fill(const int32_t* rowptr, const int32_t* col, const int32_
  * also used for the query graphs, lightning_model.py:84-85).  Rows must have ascending edge_col. */
 int desco_shmp_edge_types(const int32_t* edge_ptr, const int32_t* edge_col, int32_t num_rows, uint8_t* edge_tri,
                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * SHMP neighborhood counting (forward)
+ * Replaces: SAGEConv (gnn_model.py:362-404), BaseGNNCore.forward as expanded by to_hetero_old
+ *           (gnn_model.py:230-277, lightning_model.py:371-421), BaseGNN.forward (gnn_model.py:58-109).
+ *
+ * Input: a packed batch (see desco_partition_fill).  hetero = 1: target neighborhoods (node types count/canonical,
+ * canonical = last row of each neighborhood, 6 relations); hetero = 0: query graphs (one node type, 2 relations, no
+ * anchor_mlp).  pyg_batch_size: size of the collated PyG batches the reference would have formed (config.py:255,
+ * default 512; 0 = the whole input is one batch) - needed only to reproduce SAGEConv's remove_self_loops on the
+ * bipartite relations (gnn_model.py:389-390), see DESIGN.md "reference quirks".
+ * feat: [num_rows, input_dim] node features or NULL for ZeroNodeFeat (workload.py:431-440).
+ *
+ * Weight blobs (float32, K-major = transposed nn.Linear weights; built by desco_b200.gnn_model.pack_*):
+ *   w_pre     per node type t in (count, canonical) [hetero] or (union_node): Wpre_t[input_dim][64], bpre_t[64]
+ *   w_layers  per layer, desco_shmp_layer_weight_floats() floats:
+ *               Wc[192][64]   = [ (U_m W_cc_tri)^T ; (U_m W_cc_tride)^T ; U_h^T ]          count destinations
+ *               bias_c[64]    = U_m (sum of the biases of the 4 relations into count) + u
+ *               Cw[64][128]   = [ (U_m W_ac_tri)^T | (U_m W_ac_tride)^T ]                  canonical -> count
+ *               Wa[192][64], bias_a[64]                                                     canonical destinations
+ *             (U = updates[l] weight split as [U_m | U_h], gnn_model.py:264; single-type graphs use Wc/bias_c only)
+ *   w_readout Wanc[576][576], banc[576], P0[576][64], b0[64], P1[64][64], b1[64], P2[64][256], b2[256],
+ *             P3[256][64], b3[64]                                    (anchor_mlp + post_mp, gnn_model.py:40-53)
+ * out_emb: [num_neighborhoods, 64].  precision: DESCO_PRECISION_*.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int64_t desco_shmp_workspace_bytes(int32_t num_rows, int32_t num_neighborhoods, int32_t layers);
+int64_t desco_shmp_layer_weight_floats(void);
+int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
+                       int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
+                       const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
+                       const float* w_readout, int32_t layers, int32_t hidden, float* out_emb, void* workspace,
+                       int64_t workspace_bytes, int32_t precision, void* stream);
+
+/* Query-conditioned count head.  Replaces embed_to_count / the per-query loop of graph_to_count
+ * (lightning_model.py:176-222, count_model :127-131):  pred[g,q] = count_model(cat(emb_target[g], emb_query[q])),
+ * count = 2^pred - 1.  w_head: W1a[64][256] (target half of Linear(128,256)), W1b[64][256] (query half), b1[256],
+ * w2[256], b2[1].  out_pred / out_count: [G, Q], either may be NULL. */
+int64_t desco_count_head_workspace_bytes(int32_t num_neighborhoods, int32_t num_queries);
+int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const float* emb_query, int32_t num_queries,
+                     const float* w_head, int32_t hidden, float* out_pred, float* out_count, void* workspace,
+                     int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,130 @@
+"""GPU parity: SHMP neighborhood counting (through the C ABI) vs the oracle on identical seeded weights.
+
+Tolerance (north_star): fp32 path 1e-4, checked as |d| <= tol * max(1, |ref|) on counts AND |d| <= tol on the
+pre-exponent (random-init counts are ~ -0.03, a pure relative test is ill-conditioned - SURVEY.md section 7)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from desco_b200.graph import gen_cox2_shaped, gen_enzymes_shaped, gen_imdb_shaped, gen_mutag_shaped, gen_syn1827_shaped
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _models(seed=0, bias_shift=None):
+    from desco_b200.lightning_model import NeighborhoodCountingModel, STANDARD_QUERY_IDS
+    from oracle import model as M
+
+    torch.manual_seed(seed)
+    om = M.NeighborhoodCountingModel().eval()
+    if bias_shift is not None:  # spread the pre-exponent over a useful range (hard part 1)
+        with torch.no_grad():
+            om.count_model[2].bias.fill_(bias_shift)
+            om.count_model[2].weight.mul_(40.0)
+    pm = NeighborhoodCountingModel().eval()
+    pm.load_state_dict(om.state_dict())
+    pm = pm.cuda()
+    pm.set_queries(STANDARD_QUERY_IDS)
+    return om, pm
+
+
+def _check(om, pm, b_np, pyg_bs=None, tol=TOL):
+    from desco_b200.data import NeighborhoodBatch
+    from oracle import model as M
+
+    with torch.no_grad():
+        ref_pred = om.pre_exponent(b_np, M.query_batch(), pyg_batch_size=pyg_bs)
+    ref_count = 2 ** ref_pred - 1
+    batch = NeighborhoodBatch.from_numpy(b_np)
+    pm.set_pyg_batch_size(pyg_bs or 0)
+    with torch.no_grad():
+        count, pred = pm.embed_to_count((pm.emb_model(batch), pm.get_query_emb()), want_pred=True)
+    torch.cuda.synchronize()
+    dp = (pred.cpu() - ref_pred).abs().max().item()
+    dc = ((count.cpu() - ref_count).abs() / ref_count.abs().clamp(min=1.0)).max().item()
+    assert dp <= tol, f"pre-exponent diff {dp}"
+    assert dc <= tol, f"count diff {dc}"
+    return dp, dc
+
+
+def test_query_embeddings_match_oracle(cuda_device):
+    from oracle import model as M
+
+    om, pm = _models(0)
+    with torch.no_grad():
+        ref = om.get_query_emb(M.query_batch())
+        got = pm.get_query_emb().cpu()
+    assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_shmp_matches_reference_leaf_golden(cuda_device, golden_dir):
+    """Fixture produced with the reference's own SAGEConv / Linear leaves (tests/golden/make_golden.py)."""
+    from desco_b200.data import NeighborhoodBatch
+    from desco_b200.lightning_model import NeighborhoodCountingModel, STANDARD_QUERY_IDS
+    from oracle import model as M
+
+    z = np.load(os.path.join(golden_dir, "shmp_hetero_ref.npz"))
+    torch.manual_seed(int(z["seed"]))
+    om = M.NeighborhoodCountingModel().eval()
+    pm = NeighborhoodCountingModel().eval()
+    pm.load_state_dict(om.state_dict())
+    pm = pm.cuda()
+    pm.set_queries(STANDARD_QUERY_IDS)
+    b = {k[2:]: z[k] for k in z.files if k.startswith("b_")}
+    with torch.no_grad():
+        emb = pm.graph_to_embed(NeighborhoodBatch.from_numpy(b)).cpu()
+        count = pm.graph_to_count(NeighborhoodBatch.from_numpy(b)).cpu()
+    assert (emb - torch.from_numpy(z["target_emb"])).abs().max().item() <= TOL
+    assert (pm.get_query_emb().cpu() - torch.from_numpy(z["query_emb"])).abs().max().item() <= TOL
+    assert (count - torch.from_numpy(z["count"])).abs().max().item() <= TOL
+
+
+@pytest.mark.parametrize("gen,kw", [(gen_mutag_shaped, dict(num_graphs=40)), (gen_cox2_shaped, dict(num_graphs=30)),
+                                    (gen_enzymes_shaped, dict(num_graphs=40)), (gen_imdb_shaped, dict(num_graphs=30)),
+                                    (gen_syn1827_shaped, dict(stride=200))])
+def test_shmp_counts_match_oracle(cuda_device, gen, kw):
+    from oracle import partition as P
+
+    om, pm = _models(1)
+    b = P.partition_dataset(gen(seed=4, **kw), 4)
+    _check(om, pm, b)
+
+
+def test_shmp_counts_match_oracle_wide_range(cuda_device):
+    """Count-head scaled so pred spans several units: exercises 2**pred and the relative check for real."""
+    from oracle import partition as P
+
+    om, pm = _models(2, bias_shift=3.0)
+    b = P.partition_dataset(gen_enzymes_shaped(seed=5, num_graphs=30), 4)
+    dp, dc = _check(om, pm, b, tol=2e-4)
+
+
+def test_pyg_batch_quirk_is_reproduced(cuda_device):
+    """SAGEConv.remove_self_loops on bipartite relations (gnn_model.py:389-390) depends on the collated batch size."""
+    from oracle import partition as P
+
+    om, pm = _models(3)
+    b = P.partition_dataset(gen_mutag_shaped(seed=6, num_graphs=30), 4)
+    for bs in (None, 7, 64):
+        _check(om, pm, b, pyg_bs=bs)
+
+
+def test_shmp_node_order_invariance(cuda_device):
+    """Property at full config-2 size: counts do not depend on which neighborhoods share a batch (no quirk chunks)."""
+    from desco_b200.data import DeviceCSR, partition_batch
+    from desco_b200.graph import first_nonempty_centres
+
+    _, pm = _models(4)
+    pm.set_pyg_batch_size(1)  # every neighborhood its own PyG batch: quirk applies uniformly, batches independent
+    csr = gen_enzymes_shaped(seed=0)
+    d = DeviceCSR.from_host(csr)
+    centres = torch.as_tensor(first_nonempty_centres(csr, 4096), device="cuda")
+    with torch.no_grad():
+        full = pm.graph_to_count(partition_batch(d, centres, 4))
+        perm = torch.randperm(4096, device="cuda")
+        shuf = pm.graph_to_count(partition_batch(d, centres[perm], 4))
+    assert full.shape == (4096, 29)
+    assert (full[perm] - shuf).abs().max().item() <= 1e-6
