@@ -47,6 +47,31 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// FFMA tile GEMM shared by the SHMP / gossip / readout kernels: 256 threads, thread (ty,tx) owns rows ty*4..+3 and
+// columns tx*4..+3 of a 64 x 64 output tile.
+// acc[4][4] += sA[ty*4+i][0..K) . sW[0..K)[tx*4+j]
+template <int K, int LD, int LDW = 64>
+__device__ __forceinline__ void tile_gemm(const float* sA, const float* sW, int ty, int tx, float acc[4][4]) {
+#pragma unroll 2
+  for (int k4 = 0; k4 < K; k4 += 4) {
+    float4 a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(sA + (ty * 4 + i) * LD + k4);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 w = *reinterpret_cast<const float4*>(sW + (k4 + kk) * LDW + tx * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+        acc[i][0] = fmaf(av, w.x, acc[i][0]);
+        acc[i][1] = fmaf(av, w.y, acc[i][1]);
+        acc[i][2] = fmaf(av, w.z, acc[i][2]);
+        acc[i][3] = fmaf(av, w.w, acc[i][3]);
+      }
+    }
+  }
+}
+
 static inline int desco_num_sms() {
   static int sms = 0;
   if (!sms) {

@@ -144,29 +144,6 @@ __device__ __forceinline__ void load_weights(float* sW, const float* __restrict_
   for (int i = threadIdx.x; i < KC * F / 4; i += THREADS) dst[i] = src[i];
 }
 
-// acc[4][4] += sA[ty*4+i][0..K) . sW[0..K)[tx*4+j]
-template <int K, int LD>
-__device__ __forceinline__ void tile_gemm(const float* sA, const float* sW, int ty, int tx, float acc[4][4]) {
-#pragma unroll 2
-  for (int k4 = 0; k4 < K; k4 += 4) {
-    float4 a[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(sA + (ty * 4 + i) * LD + k4);
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const float4 w = *reinterpret_cast<const float4*>(sW + (k4 + kk) * F + tx * 4);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-        acc[i][0] = fmaf(av, w.x, acc[i][0]);
-        acc[i][1] = fmaf(av, w.y, acc[i][1]);
-        acc[i][2] = fmaf(av, w.z, acc[i][2]);
-        acc[i][3] = fmaf(av, w.w, acc[i][3]);
-      }
-    }
-  }
-}
-
 __global__ void __launch_bounds__(THREADS, 2) shmp_layer_kernel(const LayerArgs p) {
   extern __shared__ __align__(16) float smem[];
   float* sA = smem;                    // [TM][LDA]

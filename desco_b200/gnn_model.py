@@ -191,3 +191,125 @@ class BaseGNN(nn.Module):
                 _ptr(w["readout"]), core.layer_num, core.hidden_dim, _ptr(out), _ptr(work), wbytes,
                 PRECISION[self.precision], _stream()), "desco_shmp_forward")
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# gossip
+# ---------------------------------------------------------------------------------------------
+
+
+class GossipConv(nn.Module):
+    """``gnn_model.py:280-359`` parameter holder (lin_com, lin_update, lin_gate); arithmetic in csrc/gossip.cu."""
+
+    def __init__(self, in_channels, out_channels, emb_channels, aggr="add", **kwargs):
+        super().__init__()
+        assert aggr == "add"
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_com = nn.Linear(in_channels, out_channels)
+        self.lin_update = nn.Linear(out_channels + in_channels, out_channels)
+        self.lin_gate = nn.Sequential(
+            nn.Linear(emb_channels, out_channels), nn.Sigmoid(), nn.Linear(out_channels, 1), nn.Sigmoid(), nn.LeakyReLU()
+        )
+
+    def __repr__(self):
+        return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)
+
+
+class GossipCore(nn.Module):
+    """GOSSIP configuration of ``BaseGNNCore`` (``gnn_model.py:131-134,146-183``): pre_mp + 2 GossipConv."""
+
+    def __init__(self, input_dim, hidden_dim, args, emb_channels):
+        super().__init__()
+        if args.conv_type != "GOSSIP" or args.layer_num != 2 or hidden_dim != 64 or emb_channels != 64 or input_dim != 1:
+            raise NotImplementedError("the gossip kernels are specialised for config.py:312-322 defaults "
+                                      "(GOSSIP, 2 layers, hidden 64, query embedding 64, input_dim 1)")
+        self.pre_mp = nn.Sequential(nn.Linear(input_dim, hidden_dim))
+        self.convs = nn.ModuleList()
+        for l in range(args.layer_num):
+            cin = hidden_dim + emb_channels if l == 0 else hidden_dim
+            self.convs.append(GossipConv(cin, hidden_dim, emb_channels))
+        self.post_input_dim = hidden_dim * args.layer_num + hidden_dim + emb_channels
+        self.input_pattern_emb = True
+
+
+def pack_gossip_weights(base: "GossipBaseGNN") -> Dict[str, torch.Tensor]:
+    """Fold the rank-structured layer-0 / x0 terms (DESIGN.md "Gossip kernels") in fp64 and lay the rest out K-major."""
+    core = base.gnn_core
+    F = 64
+    dev = base.post_mp[0].weight.device
+    d = lambda t: t.detach().to("cpu", torch.float64)
+    w_pre, b_pre = d(core.pre_mp[0].weight)[:, 0], d(core.pre_mp[0].bias)
+    c0, c1 = core.convs[0], core.convs[1]
+    Wcom0, bcom0 = d(c0.lin_com.weight), d(c0.lin_com.bias)
+    Wcom0q, Wcom0c = Wcom0[:, :F], Wcom0[:, F:]
+    Wup0, bup0 = d(c0.lin_update.weight), d(c0.lin_update.bias)
+    Wup0a, Wup0q, Wup0c = Wup0[:, :F], Wup0[:, F:2 * F], Wup0[:, 2 * F:]
+    Wcom1, bcom1 = d(c1.lin_com.weight), d(c1.lin_com.bias)
+    Wup1, bup1 = d(c1.lin_update.weight), d(c1.lin_update.bias)
+    Wup1a, Wup1b = Wup1[:, :F], Wup1[:, F:]
+    P0, b0 = d(base.post_mp[0].weight), d(base.post_mp[0].bias)
+    P0q, P0c, P0x1, P0x2 = P0[:, :F], P0[:, F:2 * F], P0[:, 2 * F:3 * F], P0[:, 3 * F:]
+    pad3 = torch.zeros(3, dtype=torch.float64)
+    wq = [(Wup0a @ Wcom0q).t().contiguous().flatten(), Wup0a @ (Wcom0c @ b_pre + bcom0),
+          Wup0q.t().contiguous().flatten(), Wup0c @ b_pre + bup0,
+          P0q.t().contiguous().flatten(), P0c @ b_pre + b0]
+    for c in (c0, c1):
+        wq += [d(c.lin_gate[0].weight).t().contiguous().flatten(), d(c.lin_gate[0].bias), d(c.lin_gate[2].weight)[0],
+               d(c.lin_gate[2].bias), pad3]
+    wg = [Wup0a @ (Wcom0c @ w_pre), Wup0c @ w_pre, P0c @ w_pre, Wup1a @ bcom1, bup1,
+          torch.cat([(Wup1a @ Wcom1).t(), Wup1b.t()], 0).contiguous().flatten(),
+          torch.cat([P0x1.t(), P0x2.t()], 0).contiguous().flatten(),
+          d(base.post_mp[3].weight).t().contiguous().flatten(), d(base.post_mp[3].bias),
+          d(base.post_mp[5].weight).t().contiguous().flatten(), d(base.post_mp[5].bias),
+          d(base.post_mp[7].weight)[0], d(base.post_mp[7].bias), pad3]
+    f32 = lambda parts: torch.cat(parts).to(torch.float32).to(dev).contiguous()
+    out = {"wq": f32(wq), "wg": f32(wg)}
+    lib = _lib.load()
+    assert out["wq"].numel() == lib.desco_gossip_query_weight_floats(), (out["wq"].numel(), lib.desco_gossip_query_weight_floats())
+    assert out["wg"].numel() == lib.desco_gossip_weight_floats(), (out["wg"].numel(), lib.desco_gossip_weight_floats())
+    return out
+
+
+class GossipBaseGNN(nn.Module):
+    """``BaseGNN`` with ``baseline="gossip"`` (``gnn_model.py:18-109``): per-node output, no pooling, no anchor."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, args, **kwargs):
+        super().__init__()
+        assert output_dim == 1
+        self.args, self.kwargs = args, kwargs
+        self.gnn_core = GossipCore(input_dim, hidden_dim, args, kwargs.get("emb_channels", 64))
+        p = self.gnn_core.post_input_dim
+        self.anchor_mlp = nn.Sequential(nn.Linear(p, p), nn.LeakyReLU(0.1))  # in the reference state dict, unused
+        self.post_mp = nn.Sequential(
+            nn.Linear(p, hidden_dim), nn.Dropout(args.dropout), nn.LeakyReLU(0.1), nn.Linear(hidden_dim, hidden_dim),
+            nn.ReLU(), nn.Linear(hidden_dim, 256), nn.ReLU(), nn.Linear(256, output_dim),
+        )
+        self.precision = "fp32"
+        self._packed = None
+        self._packed_version = None
+
+    def packed_weights(self):
+        v = _params_version(self)
+        if self._packed is None or v != self._packed_version:
+            self._packed, self._packed_version = pack_gossip_weights(self), v
+        return self._packed
+
+    def forward_all_queries(self, rowptr, col, x, query_emb, want_gates=False):
+        """out[N,Q] = x + gossip correction for every query column at once."""
+        if self.training:
+            raise NotImplementedError("gossip training (dropout 0.01 + backward) is not a CUDA path yet")
+        lib = _lib.load()
+        w = self.packed_weights()
+        dev = w["wg"].device
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        query_emb = query_emb.to(device=dev, dtype=torch.float32).contiguous()
+        N, Q = x.shape
+        out = torch.empty_like(x)
+        gates = torch.empty((2, Q), dtype=torch.float32, device=dev) if want_gates else None
+        wb = int(lib.desco_gossip_workspace_bytes(N, Q))
+        work = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.desco_gossip_forward(_ptr(rowptr), _ptr(col), N, _ptr(x), Q, _ptr(query_emb), _ptr(w["wg"]),
+                                                _ptr(w["wq"]), _ptr(out), _ptr(gates), _ptr(work), wb,
+                                                PRECISION[self.precision], _stream()), "desco_gossip_forward")
+        return (out, gates) if want_gates else out

@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import _lib
 from .data import NeighborhoodBatch, _ptr, _stream, shmp_edge_types
-from .gnn_model import QUERY_META, TARGET_META, BaseGNN
+from .gnn_model import QUERY_META, TARGET_META, BaseGNN, GossipBaseGNN
 
 STANDARD_QUERY_IDS = [6, 7, 13, 14, 15, 16, 17, 18, 29, 30, 31, 34, 35, 36, 37, 38, 40, 41, 42, 43, 44, 45, 46, 47,
                       48, 49, 50, 51, 52]  # gen_query_ids([3,4,5]), data.py:37-58
@@ -171,3 +171,60 @@ class NeighborhoodCountingModel(nn.Module):
 
     def forward(self, batch):
         return self.graph_to_count(batch)
+
+
+def default_gossip_args(**kw) -> SimpleNamespace:
+    """``config.py:312-322``."""
+    d = dict(conv_type="GOSSIP", layer_num=2, hidden_dim=64, dropout=0.01, use_hetero=False, lr=1e-3, weight_decay=0.0,
+             batch_size=256)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+class GossipCountingModel(nn.Module):
+    """``lightning_model.py:535-649``."""
+
+    def __init__(self, input_dim=1, hidden_dim=64, args=None, **kwargs):
+        super().__init__()
+        args = args or default_gossip_args(hidden_dim=hidden_dim)
+        self.hidden_dim = hidden_dim
+        kwargs["baseline"] = "gossip"
+        kwargs.setdefault("emb_channels", 64)
+        for k, v in vars(args).items():
+            if not hasattr(self, k):
+                setattr(self, k, v)
+        self.emb_model = GossipBaseGNN(input_dim, hidden_dim, 1, args, **kwargs)
+        self.kwargs = kwargs
+        self.query_emb = None
+        self.eval()
+
+    def set_query_emb(self, query_emb: torch.Tensor, query_ids=None, queries=None):
+        self.query_emb = query_emb.detach()
+
+    def graph_to_count(self, batch, query_emb=None) -> torch.Tensor:
+        """``lightning_model.py:613-628``: batch carries the target CSR (``rowptr``, ``col``) and ``x`` [N, Q]."""
+        qe = self.query_emb if query_emb is None else query_emb
+        if qe is None:
+            raise RuntimeError("call set_query_emb first")
+        g = getattr(batch, "graph", batch)
+        return self.emb_model.forward_all_queries(g.rowptr, g.col, batch.x, qe)
+
+    def predict_step(self, batch, batch_idx=0) -> torch.Tensor:
+        return self.graph_to_count(batch)
+
+    def forward(self, batch):
+        return self.graph_to_count(batch)
+
+    def _gate_value(self, query_emb) -> torch.Tensor:
+        """``lightning_model.py:640-649``: (#layers, #queries, 1)."""
+        lib = _lib.load()
+        w = self.emb_model.packed_weights()
+        dev = w["wq"].device
+        qe = query_emb.to(device=dev, dtype=torch.float32).contiguous()
+        Q = qe.shape[0]
+        qvec = torch.empty((Q, 256), dtype=torch.float32, device=dev)
+        gates = torch.empty((2, Q), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.desco_gossip_prepare_queries(_ptr(qe), Q, _ptr(w["wq"]), _ptr(qvec), _ptr(gates), _stream()),
+                       "desco_gossip_prepare_queries")
+        return gates.unsqueeze(-1)

@@ -117,6 +117,37 @@ int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const f
                      const float* w_head, int32_t hidden, float* out_pred, float* out_count, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Gossip propagation (forward)
+ * Replaces: GossipConv (gnn_model.py:280-359), the GOSSIP branch of BaseGNNCore.forward (gnn_model.py:231-260),
+ *           post_mp per node (gnn_model.py:102-103) and the per-query loop of GossipCountingModel.graph_to_count
+ *           (lightning_model.py:613-628).  2 GossipConv layers, hidden 64, input_dim 1 (config.py:312-322).
+ *
+ * rowptr/col: the target CSR (symmetric, sorted, no self loops; node ids are batch-global so "j < i" is the
+ * reference's edge_index[0] < edge_index[1], gnn_model.py:248).  x: [N, Q] neighborhood counts (row-major),
+ * query_emb: [Q, 64].  out: [N, Q] = x + gossip correction.  out_gates: [2, Q] or NULL (_gate_value,
+ * lightning_model.py:640-649).
+ * Weight blobs are built by desco_b200.gnn_model.pack_gossip_weights (layout: csrc/gossip.cu WG_* / WQ_* offsets).
+ *
+ * The three stages are also exported separately so a node-range shard [node_begin, node_end) can run layer 1 after
+ * the counts of its halo have been exchanged:  prepare_queries -> layer0 (any node range; needs x of the
+ * neighbours) -> layer1 (needs s4 of the neighbours).  qvec: [Q, 256] floats, s4: [N, Q, 4] floats.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int64_t desco_gossip_weight_floats(void);
+int64_t desco_gossip_query_weight_floats(void);
+int64_t desco_gossip_workspace_bytes(int32_t num_nodes, int32_t num_queries);
+int desco_gossip_prepare_queries(const float* query_emb, int32_t num_queries, const float* w_gossip_query, float* qvec,
+                                 float* out_gates, void* stream);
+int desco_gossip_layer0(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end, const float* x,
+                        int32_t num_queries, const float* qvec, float* s4, void* stream);
+int desco_gossip_layer1(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end, const float* s4,
+                        int32_t num_queries, const float* qvec, const float* w_gossip, float* out, int32_t precision,
+                        void* stream);
+int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_nodes, const float* x,
+                         int32_t num_queries, const float* query_emb, const float* w_gossip,
+                         const float* w_gossip_query, float* out, float* out_gates, void* workspace,
+                         int64_t workspace_bytes, int32_t precision, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
