@@ -82,6 +82,9 @@ _F = ctypes.c_float
 # name -> (restype, argtypes); must list every symbol of include/desco_b200.h (tests/test_cabi.py checks this)
 SIGNATURES = {
     "desco_version": (ctypes.c_char_p, []),
+    "desco_kernel_launches": (_L, []),
+    "desco_profile_enable": (_I, [_I]),
+    "desco_profile_read": (_I, [_VP, _VP]),
     "desco_partition_count": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "desco_partition_scan_workspace_bytes": (_L, [_I]),
     "desco_partition_scan": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP]),

@@ -21,6 +21,20 @@
     if (_e != cudaSuccess) return DESCO_ECUDA;    \
   } while (0)
 
+// launch accounting + optional per-kernel-group device timing (runtime.cu); slots: include/desco_b200.h DESCO_PROF_*
+void desco_count_launches(int n);
+class DescoProfScope {
+ public:
+  DescoProfScope(int slot, cudaStream_t s, int launches = 1);
+  ~DescoProfScope();
+
+ private:
+  int slot_, launches_;
+  cudaStream_t s_;
+  bool on_;
+  cudaEvent_t a_, b_;
+};
+
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

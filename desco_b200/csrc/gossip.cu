@@ -304,6 +304,7 @@ int desco_gossip_prepare_queries(const float* query_emb, int32_t num_queries, co
   if (num_queries < 0) return DESCO_EINVAL;
   if (num_queries == 0) return DESCO_OK;
   if (!query_emb || !w_gossip_query || !qvec) return DESCO_EINVAL;
+  desco_count_launches(1);
   gossip_query_kernel<<<num_queries, F, 0, (cudaStream_t)stream>>>(query_emb, num_queries, w_gossip_query, qvec, out_gates);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;
@@ -315,6 +316,7 @@ int desco_gossip_layer0(const int32_t* rowptr, const int32_t* col, int32_t node_
   if (node_end == node_begin || num_queries == 0) return DESCO_OK;
   if (!rowptr || !col || !x || !qvec || !s4) return DESCO_EINVAL;
   const long long threads = (long long)(node_end - node_begin) * 32;
+  DescoProfScope prof(DESCO_PROF_GOSSIP_L0, (cudaStream_t)stream);
   gossip_layer0_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       rowptr, col, node_begin, node_end, x, num_queries, qvec, reinterpret_cast<float4*>(s4));
   DESCO_LAUNCH_CHECK();
@@ -337,6 +339,7 @@ int desco_gossip_layer1(const int32_t* rowptr, const int32_t* col, int32_t node_
   const long long tiles = ((long long)(node_end - node_begin) + TM - 1) / TM;
   const long long blocks = tiles * num_queries;
   if (blocks > 0x7fffffffLL) return DESCO_ERANGE;
+  DescoProfScope prof(DESCO_PROF_GOSSIP_L1, (cudaStream_t)stream);
   gossip_layer1_kernel<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(
       rowptr, col, node_begin, node_end, reinterpret_cast<const float4*>(s4), num_queries, qvec, w_gossip, out);
   DESCO_LAUNCH_CHECK();

@@ -386,6 +386,7 @@ int launch_partition(const int32_t* rowptr, const int32_t* col, const int32_t* g
   if (!rowptr || !col || !graph_ptr || !centres || !nv || !ne || !centre_graph || !status) return DESCO_EINVAL;
   const int max_words = (max_graph_nodes + 31) / 32;
   const int sms = desco_num_sms();
+  DescoProfScope prof(DESCO_PROF_PARTITION, stream);
   if (max_words <= 64) {  // warp per centre
     const int threads = 256, groups = threads / 32;
     size_t smem = (size_t)groups * 4 * max_words * sizeof(uint32_t);
@@ -453,6 +454,7 @@ int desco_partition_scan(const int32_t* centres, const int32_t* nv, const int32_
   DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(workspace, bytes, nv, node_off, num_centres, s));
   bytes = (size_t)workspace_bytes;
   DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(workspace, bytes, ne, edge_off, num_centres, s));
+  desco_count_launches(1);
   scan_finalize_kernel<<<(num_centres + 255) / 256, 256, 0, s>>>(centres, nv, ne, keep_rank, node_off, edge_off,
                                                                 num_centres, nbh_ptr, centre_out, indicator, totals);
   DESCO_LAUNCH_CHECK();
@@ -476,6 +478,7 @@ int desco_shmp_edge_types(const int32_t* edge_ptr, const int32_t* edge_col, int3
   if (num_rows == 0) return DESCO_OK;
   const int threads = 256;
   long long total = (long long)num_rows * 32;
+  DescoProfScope prof(DESCO_PROF_PARTITION, (cudaStream_t)stream);
   edge_types_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(edge_ptr, edge_col,
                                                                                                        num_rows, edge_tri);
   DESCO_LAUNCH_CHECK();

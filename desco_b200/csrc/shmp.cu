@@ -315,6 +315,7 @@ int dense(const float* X, int ldx, const float* W, const float* bias, const floa
   if (M == 0) return DESCO_OK;
   if (K % F || N % F) return DESCO_EINVAL;
   dim3 grid((M + TM - 1) / TM, N / F);
+  DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
   dense_kernel<<<grid, THREADS, 0, s>>>(X, ldx, W, bias, R, ldr, Y, ldy, M, K, N, act, slope);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;
@@ -419,10 +420,14 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
   const int emb_ld = (layers + 1) * F;
   const int Vc = hetero ? V - G : V;
 
-  shmp_plan_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, edge_ptr, edge_col, edge_tri, G, hetero, pyg_batch_size,
-                                                       ws.row_nbh, ws.crow, ws.canon_code, ws.quirk_row);
-  DESCO_LAUNCH_CHECK();
   {
+    DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
+    shmp_plan_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, edge_ptr, edge_col, edge_tri, G, hetero,
+                                                         pyg_batch_size, ws.row_nbh, ws.crow, ws.canon_code, ws.quirk_row);
+    DESCO_LAUNCH_CHECK();
+  }
+  {
+    DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
     const long long n = (long long)V * F;
     shmp_pre_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(nbh_ptr, ws.row_nbh, V, hetero, feat, input_dim, w_pre,
                                                                ws.hA, ws.emb_a, emb_ld);
@@ -448,15 +453,22 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
     a.h_in = h_in; a.h_out = h_out; a.emb_a = ws.emb_a; a.pool = ws.pool; a.cvec = ws.cvec;
     a.Wc = wl; a.bias_c = wl + KC * F; a.Wa = wl + KC * F + F + F * 2 * F; a.bias_a = a.Wa + KC * F;
     if (hetero) {
+      DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
       shmp_cvec_kernel<<<(G + 7) / 8, 256, 0, s>>>(ws.emb_a, emb_ld, l, wl + KC * F + F, G, ws.cvec);
       DESCO_LAUNCH_CHECK();
     }
-    shmp_layer_kernel<<<grid, THREADS, smem, s>>>(a);
-    DESCO_LAUNCH_CHECK();
+    {
+      DescoProfScope prof(DESCO_PROF_SHMP_LAYER, s);
+      shmp_layer_kernel<<<grid, THREADS, smem, s>>>(a);
+      DESCO_LAUNCH_CHECK();
+    }
     float* t = h_in; h_in = h_out; h_out = t;
   }
-  shmp_pool_last_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, G, hetero, h_in, layers, ws.pool, emb_ld);
-  DESCO_LAUNCH_CHECK();
+  {
+    DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
+    shmp_pool_last_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, G, hetero, h_in, layers, ws.pool, emb_ld);
+    DESCO_LAUNCH_CHECK();
+  }
 
   // readout: [Wanc (emb_ld x emb_ld) | banc | P0 (emb_ld x F) | b0 | P1 (F x F) | b1 | P2 (F x 4F) | b2 | P3 (4F x F) | b3]
   const float* r = w_readout;
@@ -512,6 +524,7 @@ int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const f
   const size_t smem = (size_t)(HEAD_TG * (HEAD_H + 1) + HEAD_H + Q * (HEAD_H + 1)) * sizeof(float);
   if (smem > 200 * 1024) return DESCO_ERANGE;
   DESCO_CUDA_TRY(cudaFuncSetAttribute(count_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
   count_head_kernel<<<(G + HEAD_TG - 1) / HEAD_TG, THREADS, smem, s>>>(T, Bq, w2, b2, G, Q, out_pred, out_count);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;

@@ -30,6 +30,21 @@ extern "C" {
 /* Library / build identification: returns e.g. "desco_b200 0.1 sm_100a". */
 const char* desco_version(void);
 
+/* Launch accounting and live device timing (no reference counterpart; measurement support for bench.py).
+ * desco_kernel_launches: number of desco_b200 kernels launched by this process so far.
+ * desco_profile_enable(1) starts recording one CUDA-event pair (on the launching stream) around every kernel of the
+ * slots below; desco_profile_read synchronises those events and returns, per slot, the summed device milliseconds and
+ * the number of launches, then clears the record. */
+#define DESCO_PROF_PARTITION 0   /* partition count / fill kernels                 */
+#define DESCO_PROF_SHMP_LAYER 1  /* shmp_layer_kernel (one launch per SHMP layer)  */
+#define DESCO_PROF_SHMP_OTHER 2  /* plan, pre, cvec, pool, readout MLPs, count head */
+#define DESCO_PROF_GOSSIP_L0 3   /* gossip layer-0 scalar sweep                    */
+#define DESCO_PROF_GOSSIP_L1 4   /* gossip layer-1 + post_mp tile kernel           */
+#define DESCO_PROF_SLOTS 5
+int64_t desco_kernel_launches(void);
+int desco_profile_enable(int32_t on);
+int desco_profile_read(double* ms, int64_t* launches);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Canonical partition + SHMP edge typing
  * Replaces: k_neigh / k_neigh_canonical / get_neigh_canonical / get_neigh_hetero  (data.py:329-396),
