@@ -34,7 +34,7 @@ QUERY_META = (
     [("union_node", "union_triangle", "union_node"), ("union_node", "union_tride", "union_node")],
 )  # lightning_model.py:404-413
 
-PRECISION = {"fp32": 0, "tf32x3": 1, "bf16": 2}
+PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 
 
 def _key(et) -> str:

@@ -23,9 +23,10 @@ extern "C" {
 #define DESCO_MODE_CANONICAL 1 /* get_neigh_canonical subgraph_counting/data.py:353-372 (hetero_graph=False)          */
 #define DESCO_MODE_KHOP 2      /* k_neigh             subgraph_counting/data.py:329-338 (plain k-hop ball, no filter) */
 
-#define DESCO_PRECISION_FP32 0 /* fp32 FFMA everywhere: the 1e-4 parity path                                           */
-#define DESCO_PRECISION_TF32X3 1 /* tcgen05 kind::tf32, 3-pass hi/lo split: fp32-level error on the tensor pipe        */
-#define DESCO_PRECISION_BF16 2 /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate): the 1e-2 variant                */
+#define DESCO_PRECISION_FP32 0   /* fp32 FFMA everywhere (layer-by-layer kernels)                                      */
+#define DESCO_PRECISION_BF16X3 1 /* tcgen05 kind::f16, 3-pass bf16 hi/lo operand split, fp32 accumulate in TMEM:        */
+                                 /* ~3e-6 from the fp32 oracle - the default 1e-4 parity path                           */
+#define DESCO_PRECISION_BF16 2   /* tcgen05 kind::f16, single bf16 pass, fp32 accumulate: the 1e-2 variant              */
 
 /* Library / build identification: returns e.g. "desco_b200 0.1 sm_100a". */
 const char* desco_version(void);
@@ -162,6 +163,14 @@ int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_
                          int32_t num_queries, const float* query_emb, const float* w_gossip,
                          const float* w_gossip_query, float* out, float* out_gates, void* workspace,
                          int64_t workspace_bytes, int32_t precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tensor-core self test (no reference counterpart): d[128][n] = a[128][64] . B[n][64]^T on tcgen05 with the bf16 hi/lo
+ * split (passes = 1: hi.hi only, 3: hi.hi + lo.hi + hi.lo).  b_image is the pre-swizzled operand image built by
+ * desco_b200.tcpack.pack_b_operand (n*128 bytes hi, then n*128 bytes lo).  n % 32 == 0, n <= 256.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int desco_tc_selftest(const float* a, const void* b_image, int32_t n, int32_t passes, float* d, int32_t* status,
+                      void* stream);
 
 #ifdef __cplusplus
 }
