@@ -13,6 +13,7 @@
 // is one 128-vector per neighborhood.  The skip-concat (576 wide) is never materialised: the pooled sum over count
 // rows and the canonical row are accumulated layer by layer.
 #include "common.cuh"
+#include "shmp_internal.h"
 #include "../../include/desco_b200.h"
 
 namespace {
@@ -368,6 +369,7 @@ size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 struct Workspace {
   int32_t* row_nbh; int32_t* crow; uint8_t* canon_code; int32_t* quirk_row;
   float *hA, *hB, *emb_a, *pool, *cvec, *z, *t1, *t2, *t3;
+  void* fused;  // tile plan of the fused tcgen05 path
   size_t bytes;
 };
 
@@ -389,6 +391,7 @@ Workspace carve(void* base, int V, int G, int layers) {
   w.t1 = (float*)take((size_t)G * F * 4);
   w.t2 = (float*)take((size_t)G * F * 4);
   w.t3 = (float*)take((size_t)G * 4 * F * 4);
+  w.fused = (void*)take((size_t)desco_internal_shmp_fused_workspace_bytes(G));
   w.bytes = off;
   return w;
 }
@@ -402,24 +405,33 @@ int64_t desco_shmp_workspace_bytes(int32_t num_rows, int32_t num_neighborhoods, 
 }
 
 int64_t desco_shmp_layer_weight_floats(void) { return (int64_t)2 * (KC * F + F) + (int64_t)F * 2 * F; }
+int64_t desco_shmp_tc_layer_bytes(void) { return (int64_t)SHMP_TC_LAYER_BYTES; }
 
 int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
                        int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
                        const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
-                       const float* w_readout, int32_t layers, int32_t hidden, float* out_emb, void* workspace,
-                       int64_t workspace_bytes, int32_t precision, void* stream) {
+                       const void* w_layers_tc, const float* w_readout, int32_t layers, int32_t hidden, float* out_emb,
+                       void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream) {
   const int G = num_neighborhoods, V = num_rows;
   if (hidden != F || layers < 1 || input_dim < 1 || G < 0 || V < 0) return DESCO_EINVAL;
-  if (precision != DESCO_PRECISION_FP32) return DESCO_EINVAL;
+  if (precision < DESCO_PRECISION_FP32 || precision > DESCO_PRECISION_BF16) return DESCO_EINVAL;
   if (G == 0) return DESCO_OK;
-  if (!nbh_ptr || !edge_ptr || !edge_col || !edge_tri || !w_pre || !w_layers || !w_readout || !out_emb || !workspace)
-    return DESCO_EINVAL;
+  if (!nbh_ptr || !edge_ptr || !edge_col || !edge_tri || !w_pre || !w_readout || !out_emb || !workspace) return DESCO_EINVAL;
+  const bool fused = precision != DESCO_PRECISION_FP32;
+  if (fused && (!hetero || !w_layers_tc || !status)) return DESCO_EINVAL;  // tensor-core path: count/canonical batches
+  if (!fused && !w_layers) return DESCO_EINVAL;
   Workspace ws = carve(workspace, V, G, layers);
   if ((int64_t)ws.bytes > workspace_bytes) return DESCO_ENOMEM;
   cudaStream_t s = (cudaStream_t)stream;
   const int emb_ld = (layers + 1) * F;
   const int Vc = hetero ? V - G : V;
 
+  if (fused) {
+    const int rc = desco_internal_shmp_fused_layers(nbh_ptr, edge_ptr, edge_col, edge_tri, G, pyg_batch_size, feat, input_dim,
+                                                    w_pre, w_layers_tc, layers, precision == DESCO_PRECISION_BF16X3 ? 3 : 1,
+                                                    ws.emb_a, ws.pool, emb_ld, ws.fused, status, s);
+    if (rc) return rc;
+  } else {
   {
     DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
     shmp_plan_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, edge_ptr, edge_col, edge_tri, G, hetero,
@@ -469,6 +481,7 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
     shmp_pool_last_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, G, hetero, h_in, layers, ws.pool, emb_ld);
     DESCO_LAUNCH_CHECK();
   }
+  }  // layered fp32 path
 
   // readout: [Wanc (emb_ld x emb_ld) | banc | P0 (emb_ld x F) | b0 | P1 (F x F) | b1 | P2 (F x 4F) | b2 | P3 (4F x F) | b3]
   const float* r = w_readout;

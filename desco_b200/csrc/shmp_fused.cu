@@ -1,0 +1,513 @@
+// SHMP neighborhood counting, all message-passing layers fused in ONE persistent sm_100a kernel (tcgen05 + TMEM).
+//
+// Replaces (reference paths relative to fuvty/DeSCo @ 4508f7a):
+//   subgraph_counting/gnn_model.py:362-404  SAGEConv           sum-aggregate then Linear, per relation
+//   subgraph_counting/gnn_model.py:230-277  BaseGNNCore.forward as expanded by to_hetero_old (lightning_model.py:371-421)
+//   subgraph_counting/gnn_model.py:88-89,107  skip-concat + global_add_pool (written as per-layer pooled sums)
+//
+// Canonical neighborhoods are independent small graphs, so a CTA takes a TILE = a run of whole neighborhoods with at
+// most 128 rows and keeps its features on chip for all layers (the reference round-trips [V,64] through HBM twice per
+// relation per layer).  Per layer, with h the 128 x 64 tile of layer inputs:
+//   1. transform-then-aggregate (SAGEConv is linear, so sum_j (h_j W) == (sum_j h_j) W):
+//        P = h . [W_tri | W_tride | W_self]           128 x 64 x 192 GEMM on tcgen05, bf16 hi/lo operand split
+//      (three passes hi.hi + lo.hi + hi.lo, fp32 accumulation in TMEM: ~3e-6 from the fp32 oracle), weights fetched
+//      with one bulk async copy per image; the next layer's weights stream in while this layer's epilogue runs;
+//   2. while the tensor pipe works, the CUDA cores do the few canonical rows of the tile in fp32:
+//        h_a' = relu([sum_tri h_j | sum_tride h_j | h_a] . Wa + b_a),   cvec = h_a . [Cw_tri | Cw_tride];
+//   3. TMEM -> shared memory, then the segmented, edge-type-split gather runs out of shared memory:
+//        h_i' = relu(P_self[i] + sum_{j in N_tri(i)} P_tri[j] + sum_{j in N_tride(i)} P_tride[j] + cvec[type(i,a)] + b);
+//   4. h' is written back as the next layer's bf16 hi/lo A operand (swizzled) and as fp32 rows for pooling.
+// Only the pooled sums and the canonical rows ([G, (L+1)*64] each) ever leave the chip.
+#include "common.cuh"
+#include "tc05.cuh"
+#include "shmp_internal.h"
+#include "../../include/desco_b200.h"
+
+namespace {
+
+constexpr int F = 64;
+constexpr int TR = SHMP_TILE_ROWS;      // rows per tile (one UMMA M)
+constexpr int MAXC = SHMP_TILE_MAX_NBH; // neighborhoods per tile
+constexpr int NB = 3 * F;               // GEMM N: [tri | tride | self]
+constexpr int THREADS = 512;
+constexpr int NWARPS = THREADS / 32;
+constexpr int LDP = 2 * F + 4;          // row pitch (floats) of the P_tri|P_tride buffer
+constexpr int LDS_ = F + 4;             // row pitch (floats) of the fp32 staging rows (P_self, then h')
+constexpr int EDGE_CAP = 8192;          // staged edges per tile (1 byte each); larger tiles read edges from global
+constexpr int CH = SHMP_PLAN_CHUNK;     // neighborhoods per planning chunk
+
+// per-layer weight blob (bytes)
+constexpr int OFF_BHI = 0;
+constexpr int OFF_BLO = NB * 128;
+constexpr int OFF_BIASC = 2 * NB * 128;
+constexpr int OFF_BIASA = OFF_BIASC + F * 4;
+constexpr int OFF_WAT = OFF_BIASA + F * 4;        // [64 n][192 k] fp32
+constexpr int OFF_CWT = OFF_WAT + F * NB * 4;     // [128 n][64 k] fp32
+constexpr int LAYER_BYTES = OFF_CWT + 2 * F * F * 4;
+static_assert(LAYER_BYTES == SHMP_TC_LAYER_BYTES, "blob layout and header constant disagree");
+
+// shared-memory carve-up (bytes from the 1024-aligned base)
+constexpr int SM_BHI = 0;
+constexpr int SM_BLO = SM_BHI + NB * 128;
+constexpr int SM_AHI = SM_BLO + NB * 128;
+constexpr int SM_ALO = SM_AHI + TR * 128;
+constexpr int SM_P = SM_ALO + TR * 128;
+constexpr int SM_STAGE = SM_P + TR * LDP * 4;
+constexpr int SM_CIN = SM_STAGE + TR * LDS_ * 4;        // [MAXC][192]: sum_tri h_j | sum_tride h_j | h_a
+constexpr int SM_CVEC = SM_CIN + MAXC * NB * 4;         // [MAXC][128]
+constexpr int SM_CH = SM_CVEC + MAXC * 2 * F * 4;       // [MAXC][64]  h_a of the next layer
+constexpr int SM_EDGE = SM_CH + MAXC * F * 4;           // [EDGE_CAP] local col | tri << 7
+constexpr int SM_EPTR = SM_EDGE + EDGE_CAP;             // [TR + 1] int
+constexpr int SM_ROWG = SM_EPTR + ((TR + 1) * 4 + 15) / 16 * 16;  // [TR] uint8 local neighborhood of the row
+constexpr int SM_ROWCODE = SM_ROWG + TR;                // [TR] uint8: 0 none, 1 tri / 2 tride edge to canonical, 3 canonical
+constexpr int SM_NBHLO = SM_ROWCODE + TR;               // [MAXC + 1] int local first row
+constexpr int SM_QUIRK = SM_NBHLO + ((MAXC + 1) * 4 + 15) / 16 * 16;  // [MAXC] int local row or -1
+constexpr int SM_BARS = SM_QUIRK + (MAXC * 4 + 15) / 16 * 16;         // 2 mbarriers + tmem slot
+constexpr int SM_TOTAL = SM_BARS + 64;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;  // slack for the manual 1024-B alignment
+static_assert(SMEM_BYTES <= 232448, "fused SHMP kernel exceeds the 227 KB shared-memory limit");
+static_assert(SM_AHI % 1024 == 0 && SM_ALO % 1024 == 0 && SM_BLO % 1024 == 0, "UMMA tiles must be 1024-B aligned");
+
+// ------------------------------------------------------------------------------------------------------------------
+// tile plan: greedy packing of consecutive neighborhoods into tiles (<= TR rows, <= MAXC neighborhoods), per chunk of
+// CH neighborhoods, by pointer doubling over jump[g] = first neighborhood of the tile after the one starting at g.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) shmp_tile_plan_kernel(const int32_t* __restrict__ nbh_ptr, int G,
+                                                              int32_t* __restrict__ tile_start,
+                                                              int32_t* __restrict__ tile_count, int32_t* __restrict__ status) {
+  __shared__ int sP[CH + 1], sJa[CH + 1], sJb[CH + 1], sS[CH + 1];
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * CH;
+  const int n = min(CH, G - c0);
+  for (int i = tid; i <= n; i += 1024) sP[i] = nbh_ptr[c0 + i];
+  if (tid == 0) {
+    s_cnt = n;
+    sS[0] = 0;
+  }
+  __syncthreads();
+  for (int g = tid; g <= n; g += 1024) {
+    int j = n;
+    if (g < n) {
+      int lo = g + 1, hi = min(n, g + MAXC);
+      if (sP[lo] - sP[g] > TR) {
+        atomicExch(status, DESCO_ERANGE);  // a neighborhood larger than a tile: the caller must use the layered path
+      } else {
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (sP[mid] - sP[g] <= TR) lo = mid; else hi = mid - 1;
+        }
+      }
+      j = lo;
+    }
+    sJa[g] = j;
+  }
+  __syncthreads();
+  int* J = sJa;
+  int* Jn = sJb;
+  for (int len = 1; len <= n; len <<= 1) {  // invariant: sS[t] = jump^t(0) for t < len, J = jump^len
+    for (int t = tid; t < len && len + t <= n; t += 1024) sS[len + t] = J[sS[t]];
+    for (int g = tid; g <= n; g += 1024) Jn[g] = J[J[g]];
+    __syncthreads();
+    int* tmp = J; J = Jn; Jn = tmp;
+  }
+  for (int t = tid; t <= n; t += 1024)
+    if (sS[t] == n) atomicMin(&s_cnt, t);
+  __syncthreads();
+  const int count = (n == 0) ? 0 : s_cnt;
+  int32_t* out = tile_start + (size_t)blockIdx.x * (CH + 1);
+  for (int t = tid; t <= count; t += 1024) out[t] = c0 + sS[t];
+  if (tid == 0) tile_count[blockIdx.x] = count;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused layers
+// ------------------------------------------------------------------------------------------------------------------
+struct FusedArgs {
+  const int32_t* nbh_ptr; const int32_t* edge_ptr; const int32_t* edge_col; const uint8_t* edge_tri;
+  const int32_t* tile_start; const int32_t* tile_count;
+  int G, num_chunks, pyg_batch_size, layers, passes, input_dim, emb_ld;
+  const float* feat;        // [V][input_dim] or NULL (ZeroNodeFeat)
+  const float* w_pre;       // per node type (count, canonical): W[input_dim][64], b[64]
+  const uint8_t* w_layers;  // layers x LAYER_BYTES
+  float* emb_a;             // [G][emb_ld] canonical rows, all layers
+  float* pool;              // [G][emb_ld] sum over count rows, all layers
+  int32_t* status;
+};
+
+__device__ __forceinline__ void add2(float2& a, const float2 b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+__global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sBhi = smem + SM_BHI;
+  uint8_t* sAhi = smem + SM_AHI;
+  uint8_t* sAlo = smem + SM_ALO;
+  float* sP = reinterpret_cast<float*>(smem + SM_P);
+  float* sStage = reinterpret_cast<float*>(smem + SM_STAGE);
+  float* sCin = reinterpret_cast<float*>(smem + SM_CIN);
+  float* sCvec = reinterpret_cast<float*>(smem + SM_CVEC);
+  float* sCh = reinterpret_cast<float*>(smem + SM_CH);
+  uint8_t* sEdge = smem + SM_EDGE;
+  int* sEptr = reinterpret_cast<int*>(smem + SM_EPTR);
+  uint8_t* sRowG = smem + SM_ROWG;
+  uint8_t* sRowCode = smem + SM_ROWCODE;
+  int* sNbhLo = reinterpret_cast<int*>(smem + SM_NBHLO);
+  int* sQuirk = reinterpret_cast<int*>(smem + SM_QUIRK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);  // [0] weights landed, [1] MMA done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // how many tiles does this CTA own?  (tiles are dealt round-robin over the flattened (chunk, tile) list)
+  int my_tiles = 0;
+  {
+    int base = 0;
+    for (int c = 0; c < p.num_chunks; ++c) {
+      const int cnt = p.tile_count[c];
+      const int first = (int)((blockIdx.x + gridDim.x - (base % gridDim.x)) % gridDim.x);
+      if (first < cnt) my_tiles += (cnt - first + gridDim.x - 1) / gridDim.x;
+      base += cnt;
+    }
+  }
+  if (my_tiles == 0) return;
+
+  if (tid == 0) {
+    tc05::mbar_init(&bars[0], 1);
+    tc05::mbar_init(&bars[1], 1);
+    tc05::fence_mbar_init();
+  }
+  if (warp == 0) tc05::tmem_alloc(tmem_slot, 256);
+  tc05::fence_before_sync();
+  __syncthreads();
+  tc05::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t layer_image_bytes = 2 * NB * 128;
+  if (tid == 0) {  // weights of layer 0 for the first tile
+    tc05::mbar_arrive_expect_tx(&bars[0], layer_image_bytes);
+    tc05::bulk_g2s(sBhi, p.w_layers + OFF_BHI, layer_image_bytes, &bars[0]);
+  }
+  bool copy_pending = true;  // meaningful in thread 0 only
+  uint32_t wphase = 0, mphase = 0;
+  int tiles_done = 0;
+  bool timed_out = false;
+  const uint32_t idesc = tc05::make_idesc_bf16(TR, NB);
+  const int hw = lane >> 4, hl = lane & 15;  // half-warp id / lane inside the half-warp (one half-warp per row)
+
+  int chunk_base = 0;
+  for (int c = 0; c < p.num_chunks; ++c) {
+    const int cnt = p.tile_count[c];
+    const int first = (int)((blockIdx.x + gridDim.x - (chunk_base % gridDim.x)) % gridDim.x);
+    chunk_base += cnt;
+    for (int t = first; t < cnt; t += gridDim.x) {
+      const int32_t* ts = p.tile_start + (size_t)c * (CH + 1);
+      const int nb0 = ts[t], nb1 = ts[t + 1];
+      const int nc = nb1 - nb0;                    // neighborhoods in the tile
+      const int row0 = p.nbh_ptr[nb0];
+      const int R = p.nbh_ptr[nb1] - row0;         // rows in the tile
+      const int e0 = p.edge_ptr[row0];
+      const int Et = p.edge_ptr[row0 + R] - e0;
+      const bool edges_staged = Et <= EDGE_CAP;
+      if (R > TR || nc > MAXC) {  // the plan kernel has already raised DESCO_ERANGE; never overrun the tile buffers
+        ++tiles_done;
+        continue;
+      }
+
+      // ---------------- tile setup ----------------
+      __syncthreads();  // previous tile fully retired
+      if (tid <= nc) sNbhLo[tid] = p.nbh_ptr[nb0 + tid] - row0;
+      if (tid < nc) {
+        // SAGEConv.forward runs remove_self_loops on the bipartite count<->canonical relations (gnn_model.py:389-390):
+        // see shmp.cu shmp_plan_kernel / DESIGN.md "reference quirks"
+        const int g = nb0 + tid;
+        const int bs = p.pyg_batch_size > 0 ? p.pyg_batch_size : p.G;
+        const int g0 = (g / bs) * bs;
+        const int lo = p.nbh_ptr[g];
+        sQuirk[tid] = (lo - p.nbh_ptr[g0] == 2 * (g - g0)) ? (lo - row0) : -1;
+      }
+      for (int r = tid; r <= R; r += THREADS) sEptr[r] = p.edge_ptr[row0 + r] - e0;
+      if (edges_staged)
+        for (int e = tid; e < Et; e += THREADS)
+          sEdge[e] = (uint8_t)((p.edge_col[e0 + e] - row0) | (p.edge_tri[e0 + e] ? 0x80 : 0));
+      for (int i = tid; i < 2 * TR * 128 / 16; i += THREADS)  // zero both A images (rows >= R and canonical rows stay 0)
+        reinterpret_cast<uint4*>(sAhi)[i] = make_uint4(0u, 0u, 0u, 0u);
+      __syncthreads();
+      auto edge_at = [&](int e) -> int {
+        if (edges_staged) return sEdge[e];
+        return (p.edge_col[e0 + e] - row0) | (p.edge_tri[e0 + e] ? 0x80 : 0);
+      };
+      if (tid < R) {
+        int a = 0, b = nc;  // largest a with sNbhLo[a] <= tid
+        while (b - a > 1) {
+          const int mid = (a + b) >> 1;
+          if (sNbhLo[mid] <= tid) a = mid; else b = mid;
+        }
+        const int canon = sNbhLo[a + 1] - 1;
+        int code = 0;
+        if (tid == canon) {
+          code = 3;
+        } else {
+          const int eb = sEptr[tid], ee = sEptr[tid + 1];
+          if (ee > eb && tid != sQuirk[a]) {
+            const int last = edge_at(ee - 1);  // canonical = max row of its neighborhood = last entry of a sorted row
+            if ((last & 127) == canon) code = (last & 0x80) ? 1 : 2;
+          }
+        }
+        sRowG[tid] = (uint8_t)a;
+        sRowCode[tid] = (uint8_t)code;
+      }
+      __syncthreads();
+
+      // ---------------- layer-0 inputs: h0 = feat . Wpre + bpre per node type (gnn_model.py:231) ----------------
+      {
+        const float* Wc = p.w_pre;                                   // count:     [input_dim][64] then bias[64]
+        const float* Wn = p.w_pre + (size_t)(p.input_dim + 1) * F;   // canonical
+        for (int r = warp * 2 + hw; r < R; r += 2 * NWARPS) {
+          const bool canon = sRowCode[r] == 3;
+          const float* W = canon ? Wn : Wc;
+          float4 v = *reinterpret_cast<const float4*>(W + (size_t)p.input_dim * F + 4 * hl);
+          if (p.feat) {
+            for (int d = 0; d < p.input_dim; ++d) {
+              const float x = p.feat[(size_t)(row0 + r) * p.input_dim + d];
+              const float4 w = *reinterpret_cast<const float4*>(W + (size_t)d * F + 4 * hl);
+              v.x = fmaf(x, w.x, v.x); v.y = fmaf(x, w.y, v.y); v.z = fmaf(x, w.z, v.z); v.w = fmaf(x, w.w, v.w);
+            }
+          }
+          if (canon) {
+            *reinterpret_cast<float4*>(sCh + sRowG[r] * F + 4 * hl) = v;
+          } else {
+            *reinterpret_cast<float4*>(sStage + r * LDS_ + 4 * hl) = v;
+            __align__(8) __nv_bfloat16 hi[4], lo[4];
+            tc05::split_bf16(v.x, hi[0], lo[0]); tc05::split_bf16(v.y, hi[1], lo[1]);
+            tc05::split_bf16(v.z, hi[2], lo[2]); tc05::split_bf16(v.w, hi[3], lo[3]);
+            const uint32_t off = tc05::sw128_offset(r, 4 * hl);
+            *reinterpret_cast<uint2*>(sAhi + off) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(sAlo + off) = *reinterpret_cast<const uint2*>(lo);
+          }
+        }
+      }
+      __syncthreads();
+
+      for (int l = 0; l <= p.layers; ++l) {
+        // ------------ pool + canonical inputs of layer l (from the fp32 rows of h^l in sStage, h_a^l in sCh) ------------
+        for (int i = warp; i < nc; i += NWARPS) {
+          const int lo = sNbhLo[i], canon = sNbhLo[i + 1] - 1;
+          float2 ps = make_float2(0.f, 0.f);
+          for (int r = lo; r < canon; ++r) add2(ps, *reinterpret_cast<const float2*>(sStage + r * LDS_ + 2 * lane));
+          const size_t gofs = (size_t)(nb0 + i) * p.emb_ld + (size_t)l * F + 2 * lane;
+          *reinterpret_cast<float2*>(p.pool + gofs) = ps;                      // global_add_pool, count rows (gnn_model.py:107)
+          const float2 ha = *reinterpret_cast<const float2*>(sCh + i * F + 2 * lane);
+          *reinterpret_cast<float2*>(p.emb_a + gofs) = ha;                     // skip-concat of the canonical row (:275)
+          if (l < p.layers) {
+            float2 vt = make_float2(0.f, 0.f), vd = vt;
+            const int quirk = sQuirk[i];
+            for (int e = sEptr[canon], ee = sEptr[canon + 1]; e < ee; ++e) {
+              const int b = edge_at(e);
+              const int j = b & 127;
+              if (j == quirk) continue;
+              const float2 v = *reinterpret_cast<const float2*>(sStage + j * LDS_ + 2 * lane);
+              if (b & 0x80) add2(vt, v); else add2(vd, v);
+            }
+            *reinterpret_cast<float2*>(sCin + i * NB + 2 * lane) = vt;
+            *reinterpret_cast<float2*>(sCin + i * NB + F + 2 * lane) = vd;
+            *reinterpret_cast<float2*>(sCin + i * NB + 2 * F + 2 * lane) = ha;
+          }
+        }
+        if (l == p.layers) break;
+        const uint8_t* wl = p.w_layers + (size_t)l * LAYER_BYTES;
+        tc05::fence_proxy_async_smem();  // A images written through the generic proxy -> visible to tcgen05.mma
+        __syncthreads();
+
+        // ------------ tensor pipe: P = h . [W_tri | W_tride | W_self]  (one thread issues) ------------
+        if (tid == 0) {
+          if (!tc05::mbar_wait(&bars[0], wphase)) timed_out = true;
+          copy_pending = false;
+          tc05::fence_after_sync();
+          const uint64_t dAhi = tc05::make_smem_desc(sAhi), dAlo = tc05::make_smem_desc(sAlo);
+          const uint64_t dBhi = tc05::make_smem_desc(sBhi), dBlo = tc05::make_smem_desc(smem + SM_BLO);
+          bool acc = false;
+          for (int pass = 0; pass < p.passes; ++pass) {
+            const uint64_t da = (pass == 1) ? dAlo : dAhi;
+            const uint64_t db = (pass == 2) ? dBlo : dBhi;
+#pragma unroll
+            for (int k = 0; k < F / 16; ++k) {
+              tc05::mma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, acc);
+              acc = true;
+            }
+          }
+          tc05::mma_commit(&bars[1]);
+        }
+        wphase ^= 1;
+
+        // ------------ CUDA cores meanwhile: canonical rows in fp32 ------------
+        {
+          const float* WaT = reinterpret_cast<const float*>(wl + OFF_WAT);
+          const float* CwT = reinterpret_cast<const float*>(wl + OFF_CWT);
+          const float* bias_a = reinterpret_cast<const float*>(wl + OFF_BIASA);
+          {  // z_a = [sum_tri | sum_tride | h_a] . Wa : thread = (n, kq), k = 32 kk + 4 kq + {0..3}
+            const int n = tid >> 3, kq = tid & 7;
+            float acc[MAXC];
+#pragma unroll
+            for (int r = 0; r < MAXC; ++r) acc[r] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < NB / 32; ++kk) {
+              const int k = 32 * kk + 4 * kq;
+              const float4 w = __ldg(reinterpret_cast<const float4*>(WaT + (size_t)n * NB + k));
+#pragma unroll
+              for (int r = 0; r < MAXC; ++r) {
+                if (r < nc) {
+                  const float4 x = *reinterpret_cast<const float4*>(sCin + r * NB + k);
+                  acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
+                }
+              }
+            }
+            const float b = bias_a[n];
+#pragma unroll
+            for (int r = 0; r < MAXC; ++r) {
+              if (r < nc) {
+                float v = acc[r];
+                v += __shfl_xor_sync(FULL_MASK, v, 1);
+                v += __shfl_xor_sync(FULL_MASK, v, 2);
+                v += __shfl_xor_sync(FULL_MASK, v, 4);
+                if (kq == 0) sCh[r * F + n] = fmaxf(v + b, 0.f);  // h_a^{l+1}; read again only after the next barrier
+              }
+            }
+          }
+          {  // cvec = h_a . [Cw_tri | Cw_tride] : thread = (n, kh), k = 16 kk + 4 kh + {0..3}
+            const int n = tid >> 2, kh = tid & 3;
+            float acc[MAXC];
+#pragma unroll
+            for (int r = 0; r < MAXC; ++r) acc[r] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < F / 16; ++kk) {
+              const int k = 16 * kk + 4 * kh;
+              const float4 w = __ldg(reinterpret_cast<const float4*>(CwT + (size_t)n * F + k));
+#pragma unroll
+              for (int r = 0; r < MAXC; ++r) {
+                if (r < nc) {
+                  const float4 x = *reinterpret_cast<const float4*>(sCin + r * NB + 2 * F + k);
+                  acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
+                }
+              }
+            }
+#pragma unroll
+            for (int r = 0; r < MAXC; ++r) {
+              if (r < nc) {
+                float v = acc[r];
+                v += __shfl_xor_sync(FULL_MASK, v, 1);
+                v += __shfl_xor_sync(FULL_MASK, v, 2);
+                if (kh == 0) sCvec[r * 2 * F + n] = v;
+              }
+            }
+          }
+        }
+
+        // ------------ accumulator: TMEM -> shared memory ------------
+        if (!tc05::mbar_wait(&bars[1], mphase)) timed_out = true;
+        mphase ^= 1;
+        tc05::fence_after_sync();
+        if (tid == 0) {  // the B images are free again: stream in the next layer's (or the next tile's layer-0) weights
+          const bool last = (tiles_done + 1 == my_tiles) && (l + 1 == p.layers);
+          if (!last) {
+            const int nl = (l + 1) % p.layers;
+            tc05::mbar_arrive_expect_tx(&bars[0], layer_image_bytes);
+            tc05::bulk_g2s(sBhi, p.w_layers + (size_t)nl * LAYER_BYTES + OFF_BHI, layer_image_bytes, &bars[0]);
+            copy_pending = true;
+          }
+        }
+        {
+          const int q = warp & 3, cg = warp >> 2;  // TMEM lane quarter of this warp, column group of 48
+          const int r = 32 * q + lane;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int c0 = cg * 48 + j * 16;
+            float v[16];
+            tc05::tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + c0, v);
+            if (r < R) {
+              float* dst = (c0 < 2 * F) ? (sP + r * LDP + c0) : (sStage + r * LDS_ + (c0 - 2 * F));
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+          }
+        }
+        tc05::fence_before_sync();
+        __syncthreads();
+
+        // ------------ segmented, edge-type-split gather out of shared memory; one half-warp per row ------------
+        {
+          const float4 bias = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(wl + OFF_BIASC) + 4 * hl);
+          for (int r = warp * 2 + hw; r < R; r += 2 * NWARPS) {
+            const int code = sRowCode[r];
+            if (code == 3) continue;  // canonical rows were done on the CUDA cores above
+            float4 acc = *reinterpret_cast<const float4*>(sStage + r * LDS_ + 4 * hl);  // P_self
+            add4(acc, bias);
+            const int eb = sEptr[r], ee = sEptr[r + 1];
+            for (int e = eb; e < ee; ++e) {
+              const int b = edge_at(e);
+              // (an edge to the canonical row adds its P row, which is exactly 0: canonical rows of A are zero and
+              //  the canonical -> count message arrives through cvec instead)
+              add4(acc, *reinterpret_cast<const float4*>(sP + (b & 127) * LDP + ((b & 0x80) ? 0 : F) + 4 * hl));
+            }
+            if (code) add4(acc, *reinterpret_cast<const float4*>(sCvec + sRowG[r] * 2 * F + (code - 1) * F + 4 * hl));
+            acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+            *reinterpret_cast<float4*>(sStage + r * LDS_ + 4 * hl) = acc;  // h^{l+1}, fp32 (pooling, canonical inputs)
+            __align__(8) __nv_bfloat16 hi[4], lo[4];
+            tc05::split_bf16(acc.x, hi[0], lo[0]); tc05::split_bf16(acc.y, hi[1], lo[1]);
+            tc05::split_bf16(acc.z, hi[2], lo[2]); tc05::split_bf16(acc.w, hi[3], lo[3]);
+            const uint32_t off = tc05::sw128_offset(r, 4 * hl);
+            *reinterpret_cast<uint2*>(sAhi + off) = *reinterpret_cast<const uint2*>(hi);  // next layer's A operand
+            *reinterpret_cast<uint2*>(sAlo + off) = *reinterpret_cast<const uint2*>(lo);
+          }
+        }
+        __syncthreads();
+      }
+      ++tiles_done;
+    }
+  }
+  if (tid == 0 && copy_pending) tc05::mbar_wait(&bars[0], wphase);  // never exit with a bulk copy in flight
+  if (timed_out) atomicExch(p.status, DESCO_ECUDA);
+  tc05::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc05::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+
+int64_t desco_internal_shmp_fused_workspace_bytes(int num_neighborhoods) {
+  const int chunks = (num_neighborhoods + CH - 1) / CH;
+  return (int64_t)(((size_t)chunks * (CH + 1) * 4 + 255) / 256 * 256 + ((size_t)chunks * 4 + 255) / 256 * 256);
+}
+
+int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col,
+                                     const uint8_t* edge_tri, int G, int pyg_batch_size, const float* feat, int input_dim,
+                                     const float* w_pre, const void* w_layers_tc, int layers, int passes, float* emb_a,
+                                     float* pool, int emb_ld, void* workspace, int32_t* status, cudaStream_t s) {
+  if (G <= 0) return DESCO_OK;
+  if (!status || !workspace || !w_layers_tc) return DESCO_EINVAL;
+  const int chunks = (G + CH - 1) / CH;
+  int32_t* tile_start = (int32_t*)workspace;
+  int32_t* tile_count = (int32_t*)((char*)workspace + ((size_t)chunks * (CH + 1) * 4 + 255) / 256 * 256);
+  {
+    DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
+    shmp_tile_plan_kernel<<<chunks, 1024, 0, s>>>(nbh_ptr, G, tile_start, tile_count, status);
+    DESCO_LAUNCH_CHECK();
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DESCO_CUDA_TRY(cudaFuncSetAttribute(shmp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  FusedArgs a;
+  a.nbh_ptr = nbh_ptr; a.edge_ptr = edge_ptr; a.edge_col = edge_col; a.edge_tri = edge_tri;
+  a.tile_start = tile_start; a.tile_count = tile_count;
+  a.G = G; a.num_chunks = chunks; a.pyg_batch_size = pyg_batch_size; a.layers = layers; a.passes = passes;
+  a.input_dim = input_dim; a.emb_ld = emb_ld;
+  a.feat = feat; a.w_pre = w_pre; a.w_layers = (const uint8_t*)w_layers_tc; a.emb_a = emb_a; a.pool = pool; a.status = status;
+  {
+    DescoProfScope prof(DESCO_PROF_SHMP_LAYER, s);
+    shmp_fused_kernel<<<desco_num_sms(), THREADS, SMEM_BYTES, s>>>(a);
+    DESCO_LAUNCH_CHECK();
+  }
+  return DESCO_OK;
+}

@@ -1,0 +1,22 @@
+// Internal interface between shmp.cu (C-ABI entry points, layered fp32 path, readout MLPs) and shmp_fused.cu
+// (the fused tcgen05 layer kernel).  Not part of the public C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SHMP_TILE_ROWS 128     /* rows per fused tile = one UMMA M                                   */
+#define SHMP_TILE_MAX_NBH 20   /* neighborhoods per fused tile (bounds the canonical-row buffers)    */
+#define SHMP_PLAN_CHUNK 2048   /* neighborhoods per tile-planning CTA; tiles never straddle chunks   */
+/* bytes of one layer in the tensor-core weight blob: B hi/lo images (2 x 192 x 128), bias_c, bias_a (64 fp32 each),
+ * WaT [64][192] fp32, CwT [128][64] fp32 */
+#define SHMP_TC_LAYER_BYTES (2 * 192 * 128 + 2 * 64 * 4 + 64 * 192 * 4 + 128 * 64 * 4)
+
+int64_t desco_internal_shmp_fused_workspace_bytes(int num_neighborhoods);
+
+// Runs every message-passing layer for a hetero (count/canonical) batch and leaves the per-layer pooled count rows
+// and canonical rows in pool / emb_a ([G][emb_ld], emb_ld = (layers + 1) * 64).  passes: 3 = bf16x3, 1 = bf16.
+// Sets *status = DESCO_ERANGE if a neighborhood does not fit a tile (results are then undefined).
+int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col,
+                                     const uint8_t* edge_tri, int G, int pyg_batch_size, const float* feat, int input_dim,
+                                     const float* w_pre, const void* w_layers_tc, int layers, int passes, float* emb_a,
+                                     float* pool, int emb_ld, void* workspace, int32_t* status, cudaStream_t s);

@@ -95,6 +95,7 @@ class NeighborhoodBatch:
     num_rows: int = 0
     num_edges: int = 0
     hetero: bool = True  # False: query graphs / homogeneous neighborhoods (single node type)
+    max_rows: int = 1 << 30  # host-known upper bound on the rows of any one neighborhood (selects the fused SHMP kernel)
     _cache: dict = field(default_factory=dict, repr=False)
 
     @property
@@ -124,9 +125,11 @@ class NeighborhoodBatch:
         V = int(d["nbh_ptr"][-1])
         node_gid = t("node_gid", np.int32) if "node_gid" in d else torch.arange(V, dtype=torch.int32, device=dev)
         centre = t("centre", np.int32) if "centre" in d else node_gid[(t("nbh_ptr", np.int64)[1:] - 1)]
+        sizes = np.diff(np.asarray(d["nbh_ptr"]))
         return NeighborhoodBatch(
             t("nbh_ptr", np.int32), node_gid, t("edge_ptr", np.int32), t("edge_col", np.int32), t("edge_tri", np.uint8),
             centre, None, None, None, len(d["nbh_ptr"]) - 1, V, int(d["edge_ptr"][-1]), hetero,
+            max_rows=int(sizes.max()) if len(sizes) else 0,
         )
 
 
@@ -176,6 +179,7 @@ def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: in
     return NeighborhoodBatch(
         nbh_ptr[: G + 1], node_gid, edge_ptr, edge_col, edge_tri, centre_out[:G], indicator[:C], cg[:C],
         graph.graph_ptr, G, V, E, hetero=(mode == MODE_HETERO),
+        max_rows=graph.max_graph_nodes,  # a neighborhood never leaves its target graph
     )
 
 

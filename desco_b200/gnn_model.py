@@ -17,6 +17,7 @@ import torch.nn as nn
 
 from . import _lib
 from .data import NeighborhoodBatch, _ptr, _stream
+from .tcpack import pack_b_operand
 
 TARGET_META = (
     ["count", "canonical"],
@@ -35,6 +36,7 @@ QUERY_META = (
 )  # lightning_model.py:404-413
 
 PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+TILE_ROWS = 128  # csrc/shmp_internal.h SHMP_TILE_ROWS
 
 
 def _key(et) -> str:
@@ -98,6 +100,7 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
         lin = core.pre_mp[0][t]
         pre += [d(lin.weight).t().contiguous().flatten(), d(lin.bias)]
     layers = []
+    tc_layers = []
     for l in range(core.layer_num):
         def fused(dst, rels):
             U, u = d(core.updates[l][dst].weight), d(core.updates[l][dst].bias)
@@ -126,11 +129,19 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
             Wa = torch.zeros(3 * F, F, dtype=torch.float64)
             bias_a = torch.zeros(F, dtype=torch.float64)
         layers += [Wc.contiguous().flatten(), bias_c, Cw.contiguous().flatten(), Wa.contiguous().flatten(), bias_a]
+        if hetero:  # tensor-core form (csrc/shmp_fused.cu): B operand rows n = output column, k contiguous
+            B = torch.cat([Wc[0:F].t(), Wc[F:2 * F].t(), Wc[2 * F:3 * F].t()], 0)  # [192][64]
+            f32b = lambda t: t.to(torch.float32).contiguous().view(torch.uint8).reshape(-1)
+            tc_layers += [pack_b_operand(B), f32b(bias_c), f32b(bias_a), f32b(Wa.t()), f32b(Cw.t())]
     ro = [d(base.anchor_mlp[0].weight).t().contiguous().flatten(), d(base.anchor_mlp[0].bias)]
     for i in (0, 3, 5, 7):
         ro += [d(base.post_mp[i].weight).t().contiguous().flatten(), d(base.post_mp[i].bias)]
     f32 = lambda parts: torch.cat(parts).to(torch.float32).to(dev).contiguous()
-    return {"pre": f32(pre), "layers": f32(layers), "readout": f32(ro)}
+    out = {"pre": f32(pre), "layers": f32(layers), "readout": f32(ro)}
+    if tc_layers:
+        out["layers_tc"] = torch.cat(tc_layers).to(dev).contiguous()
+        assert out["layers_tc"].numel() == core.layer_num * _lib.load().desco_shmp_tc_layer_bytes()
+    return out
 
 
 class BaseGNN(nn.Module):
@@ -150,7 +161,7 @@ class BaseGNN(nn.Module):
             nn.Linear(p, hidden_dim), nn.Dropout(args.dropout), nn.LeakyReLU(0.1), nn.Linear(hidden_dim, hidden_dim),
             nn.ReLU(), nn.Linear(hidden_dim, 256), nn.ReLU(), nn.Linear(256, output_dim),
         )
-        self.precision = "fp32"
+        self.precision = "bf16x3"  # tcgen05 path, ~3e-6 from the fp32 oracle; "fp32" = layer-by-layer FFMA kernels
         self.pyg_batch_size = 0  # 0: the whole NeighborhoodBatch is one collated PyG batch
         self._packed = None
         self._packed_version = None
@@ -184,13 +195,27 @@ class BaseGNN(nn.Module):
         if feat is not None:
             feat = feat.to(device=dev, dtype=torch.float32).contiguous()
             assert feat.shape == (V, core.input_dim)
+        # the tensor-core precisions keep a whole neighborhood inside one 128-row tile; query graphs (single node type)
+        # and batches that may hold larger neighborhoods take the layer-by-layer fp32 kernels
+        precision = PRECISION[self.precision]
+        if not hetero or data.max_rows > TILE_ROWS:
+            precision = 0
+        status = torch.zeros(1, dtype=torch.int32, device=dev) if precision else None
         with torch.cuda.device(dev):
             _lib.check(lib.desco_shmp_forward(
                 _ptr(data.nbh_ptr), _ptr(data.edge_ptr), _ptr(data.edge_col), _ptr(data.edge_tri), G, V, int(hetero),
                 int(self.pyg_batch_size), _ptr(feat), core.input_dim, _ptr(w["pre"]), _ptr(w["layers"]),
-                _ptr(w["readout"]), core.layer_num, core.hidden_dim, _ptr(out), _ptr(work), wbytes,
-                PRECISION[self.precision], _stream()), "desco_shmp_forward")
+                _ptr(w.get("layers_tc")), _ptr(w["readout"]), core.layer_num, core.hidden_dim, _ptr(out), _ptr(work),
+                wbytes, precision, _ptr(status), _stream()), "desco_shmp_forward")
+        if status is not None:
+            self.last_status = status  # device int32; 0 = ok.  Checked lazily (check_status) to keep the launch async.
         return out
+
+    def check_status(self) -> None:
+        """Raise if the last tensor-core forward reported a device-side error (one host sync)."""
+        st = getattr(self, "last_status", None)
+        if st is not None:
+            _lib.check(int(st.item()), "desco_shmp_forward (device status)")
 
 
 # ---------------------------------------------------------------------------------------------

@@ -40,7 +40,8 @@ def batch_from_networkx(neighs: List, type_key: str = "type", device="cuda", typ
     V = nbh_ptr[-1]
     ng = t(gid)
     return NeighborhoodBatch(t(nbh_ptr), ng, ep, ec, tri, ng[(t(nbh_ptr)[1:] - 1).long()] if V else ng, None, None, None,
-                             len(neighs), V, len(edge_col), hetero=bool(hetero))
+                             len(neighs), V, len(edge_col), hetero=bool(hetero),
+                             max_rows=max((b - a for a, b in zip(nbh_ptr[:-1], nbh_ptr[1:])), default=0))
 
 
 def NetworkxToHetero(nx_graph, type_key: str = "type", feat_key: str = "feat", device="cuda") -> NeighborhoodBatch:

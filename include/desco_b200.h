@@ -114,15 +114,24 @@ int desco_shmp_edge_types(const int32_t* edge_ptr, const int32_t* edge_col, int3
  *             (U = updates[l] weight split as [U_m | U_h], gnn_model.py:264; single-type graphs use Wc/bias_c only)
  *   w_readout Wanc[576][576], banc[576], P0[576][64], b0[64], P1[64][64], b1[64], P2[64][256], b2[256],
  *             P3[256][64], b3[64]                                    (anchor_mlp + post_mp, gnn_model.py:40-53)
+ *   w_layers_tc  tensor-core form of w_layers for precision BF16X3 / BF16 (hetero batches only), per layer
+ *             desco_shmp_tc_layer_bytes() bytes: the [tri | tride | self] weights as a 192 x 64 K-major operand, split in
+ *             bf16 hi / lo and pre-swizzled (SWIZZLE_128B shared-memory images, desco_b200.tcpack), then fp32
+ *             bias_c[64], bias_a[64], Wa^T[64][192], Cw^T[128][64].  May be NULL for precision FP32 (then w_layers is
+ *             required); w_layers may be NULL for the tensor-core precisions.
  * out_emb: [num_neighborhoods, 64].  precision: DESCO_PRECISION_*.
+ * status (device int32, caller-zeroed; required for the tensor-core precisions): DESCO_ERANGE when a neighborhood has
+ * more than 128 rows - the fused kernel keeps a whole neighborhood in one 128-row tile - and the caller must rerun
+ * with DESCO_PRECISION_FP32 (the layer-by-layer path has no size limit).
  * ---------------------------------------------------------------------------------------------------------------- */
 int64_t desco_shmp_workspace_bytes(int32_t num_rows, int32_t num_neighborhoods, int32_t layers);
 int64_t desco_shmp_layer_weight_floats(void);
+int64_t desco_shmp_tc_layer_bytes(void);
 int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
                        int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
                        const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
-                       const float* w_readout, int32_t layers, int32_t hidden, float* out_emb, void* workspace,
-                       int64_t workspace_bytes, int32_t precision, void* stream);
+                       const void* w_layers_tc, const float* w_readout, int32_t layers, int32_t hidden, float* out_emb,
+                       void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream);
 
 /* Query-conditioned count head.  Replaces embed_to_count / the per-query loop of graph_to_count
  * (lightning_model.py:176-222, count_model :127-131):  pred[g,q] = count_model(cat(emb_target[g], emb_query[q])),

@@ -31,7 +31,7 @@ def _models(seed=0, bias_shift=None):
     return om, pm
 
 
-def _check(om, pm, b_np, pyg_bs=None, tol=TOL):
+def _check(om, pm, b_np, pyg_bs=None, tol=TOL, precision="bf16x3"):
     from desco_b200.data import NeighborhoodBatch
     from oracle import model as M
 
@@ -40,9 +40,11 @@ def _check(om, pm, b_np, pyg_bs=None, tol=TOL):
     ref_count = 2 ** ref_pred - 1
     batch = NeighborhoodBatch.from_numpy(b_np)
     pm.set_pyg_batch_size(pyg_bs or 0)
+    pm.set_precision(precision)
     with torch.no_grad():
         count, pred = pm.embed_to_count((pm.emb_model(batch), pm.get_query_emb()), want_pred=True)
     torch.cuda.synchronize()
+    pm.emb_model.check_status()
     # random-init weights push pred of big (Syn-shaped, 300-node) neighborhoods to ~500, where the fp32 oracle itself is
     # 6e-4 away from an fp64 run: the pre-exponent check is relative above 1, and counts (2**pred, overflowing fp32
     # beyond pred = 128) are compared where the exponent is in a sane range.
@@ -90,11 +92,66 @@ def test_shmp_matches_reference_leaf_golden(cuda_device, golden_dir):
                                     (gen_enzymes_shaped, dict(num_graphs=40)), (gen_imdb_shaped, dict(num_graphs=30)),
                                     (gen_syn1827_shaped, dict(stride=200))])
 def test_shmp_counts_match_oracle(cuda_device, gen, kw):
+    """Both 1e-4 paths: the fused tcgen05 kernel (bf16 hi/lo split, 3 passes) and the layer-by-layer fp32 kernels.
+    (Syn-shaped neighborhoods exceed a 128-row tile, so that batch takes the fp32 kernels in both runs.)"""
     from oracle import partition as P
 
     om, pm = _models(1)
     b = P.partition_dataset(gen(seed=4, **kw), 4)
-    _check(om, pm, b)
+    _check(om, pm, b, precision="bf16x3")
+    _check(om, pm, b, precision="fp32")
+
+
+def test_shmp_bf16_single_pass_variant(cuda_device):
+    """The separately-stated bf16 variant (one tensor-core pass): 1e-2."""
+    from oracle import partition as P
+
+    om, pm = _models(5)
+    b = P.partition_dataset(gen_enzymes_shaped(seed=6, num_graphs=40), 4)
+    dp, dc = _check(om, pm, b, tol=1e-2, precision="bf16")
+    assert dp > 1e-6  # it really is the reduced-precision path
+
+
+def test_fused_path_tiny_and_mixed_neighborhoods(cuda_device):
+    """Tiles capped by the neighborhood count (2-row neighborhoods), single-neighborhood batches, ragged tails."""
+    import networkx as nx
+
+    from desco_b200.graph import csr_from_networkx
+    from oracle import partition as P
+
+    om, pm = _models(6)
+    gs = [nx.path_graph(2) for _ in range(70)] + [nx.complete_graph(9), nx.star_graph(30), nx.cycle_graph(5)]
+    gs += [nx.path_graph(2) for _ in range(5)] + [nx.complete_graph(40)]
+    b = P.partition_dataset(csr_from_networkx(gs), 4)
+    for bs in (None, 3, 512):
+        _check(om, pm, b, pyg_bs=bs)
+    one = P.partition_dataset(csr_from_networkx([nx.complete_graph(40)]), 4, centres=np.array([39]))
+    _check(om, pm, one)
+
+
+def test_fused_path_reports_oversize_neighborhoods(cuda_device):
+    """A neighborhood above 128 rows cannot be a fused tile: the Python surface routes the batch to the fp32 kernels,
+    and the raw C ABI reports DESCO_ERANGE through the device status word instead of computing garbage silently."""
+    import networkx as nx
+
+    from desco_b200 import _lib
+    from desco_b200.data import NeighborhoodBatch
+    from desco_b200.graph import csr_from_networkx
+    from oracle import partition as P
+
+    om, pm = _models(7)
+    b = P.partition_dataset(csr_from_networkx([nx.path_graph(200), nx.path_graph(6)]), 4, centres=np.array([199, 205]))
+    b2 = P.partition_dataset(csr_from_networkx([nx.star_graph(160)]), 4, centres=np.array([160]))
+    assert np.diff(b2["nbh_ptr"]).max() == 161
+    _check(om, pm, b2)  # falls back to fp32 on its own
+    batch = NeighborhoodBatch.from_numpy(b2)
+    batch.max_rows = 64  # lie about the bound: the kernel must notice
+    pm.set_precision("bf16x3")
+    with torch.no_grad():
+        pm.emb_model(batch)
+    torch.cuda.synchronize()
+    with pytest.raises(_lib.DescoError):
+        pm.emb_model.check_status()
 
 
 def test_shmp_counts_match_oracle_wide_range(cuda_device):
