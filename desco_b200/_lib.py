@@ -102,6 +102,7 @@ SIGNATURES = {
     "desco_gossip_prepare_queries": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "desco_gossip_layer0": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP]),
     "desco_gossip_layer1": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP]),
+    "desco_shmp_fused_phase_cycles": (_I, [_VP, _I]),
     "desco_tc_selftest": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
     "desco_gossip_forward": (_I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _L, _I, _VP]),
 }

@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(1024) shmp_tile_plan_kernel(const int32_t* __r
 // ------------------------------------------------------------------------------------------------------------------
 // fused layers
 // ------------------------------------------------------------------------------------------------------------------
+// phase timing (thread 0 of every CTA accumulates its own clock64 deltas; read with desco_shmp_fused_phase_cycles)
+enum { PH_SETUP = 0, PH_POOL, PH_ISSUE, PH_CANON, PH_WAIT_MMA, PH_T2S, PH_GATHER, PH_COUNT };
+__device__ unsigned long long g_phase_cycles[PH_COUNT];
+
 struct FusedArgs {
   const int32_t* nbh_ptr; const int32_t* edge_ptr; const int32_t* edge_col; const uint8_t* edge_tri;
   const int32_t* tile_start; const int32_t* tile_count;
@@ -140,7 +144,9 @@ __device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.
 
 __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-B alignment computed as an OFFSET from the __shared__ symbol, so the compiler keeps the shared address space
+  // (LDS/STS); casting through uintptr_t would turn every access into a generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sBhi = smem + SM_BHI;
   uint8_t* sAhi = smem + SM_AHI;
   uint8_t* sAlo = smem + SM_ALO;
@@ -215,6 +221,14 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
       }
 
       // ---------------- tile setup ----------------
+      long long tick = clock64();
+      auto lap = [&](int phase) {
+        if (tid == 0) {
+          const long long now = clock64();
+          atomicAdd(&g_phase_cycles[phase], (unsigned long long)(now - tick));
+          tick = now;
+        }
+      };
       __syncthreads();  // previous tile fully retired
       if (tid <= nc) sNbhLo[tid] = p.nbh_ptr[nb0 + tid] - row0;
       if (tid < nc) {
@@ -288,36 +302,52 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         }
       }
       __syncthreads();
+      lap(PH_SETUP);
 
       for (int l = 0; l <= p.layers; ++l) {
+        // this thread's slice of the canonical-row weights of layer l: issued now, consumed after the pool phase
+        const uint8_t* wl = p.w_layers + (size_t)(l < p.layers ? l : 0) * LAYER_BYTES;
+        const int kq = tid & 7, kh = tid & 3;
+        float4 wa[NB / 32], wc[F / 16];
+        float bias_an = 0.f;
+        if (l < p.layers) {
+          const float* WaT = reinterpret_cast<const float*>(wl + OFF_WAT) + (size_t)(tid >> 3) * NB + 4 * kq;
+          const float* CwT = reinterpret_cast<const float*>(wl + OFF_CWT) + (size_t)(tid >> 2) * F + 4 * kh;
+#pragma unroll
+          for (int kk = 0; kk < NB / 32; ++kk) wa[kk] = __ldg(reinterpret_cast<const float4*>(WaT + 32 * kk));
+#pragma unroll
+          for (int kk = 0; kk < F / 16; ++kk) wc[kk] = __ldg(reinterpret_cast<const float4*>(CwT + 16 * kk));
+          bias_an = __ldg(reinterpret_cast<const float*>(wl + OFF_BIASA) + (tid >> 3));
+        }
         // ------------ pool + canonical inputs of layer l (from the fp32 rows of h^l in sStage, h_a^l in sCh) ------------
-        for (int i = warp; i < nc; i += NWARPS) {
+        for (int i = warp * 2 + hw; i < nc; i += 2 * NWARPS) {  // one half-warp per neighborhood, 4 features per lane
           const int lo = sNbhLo[i], canon = sNbhLo[i + 1] - 1;
-          float2 ps = make_float2(0.f, 0.f);
-          for (int r = lo; r < canon; ++r) add2(ps, *reinterpret_cast<const float2*>(sStage + r * LDS_ + 2 * lane));
-          const size_t gofs = (size_t)(nb0 + i) * p.emb_ld + (size_t)l * F + 2 * lane;
-          *reinterpret_cast<float2*>(p.pool + gofs) = ps;                      // global_add_pool, count rows (gnn_model.py:107)
-          const float2 ha = *reinterpret_cast<const float2*>(sCh + i * F + 2 * lane);
-          *reinterpret_cast<float2*>(p.emb_a + gofs) = ha;                     // skip-concat of the canonical row (:275)
+          float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+          for (int r = lo; r < canon; ++r) add4(ps, *reinterpret_cast<const float4*>(sStage + r * LDS_ + 4 * hl));
+          const size_t gofs = (size_t)(nb0 + i) * p.emb_ld + (size_t)l * F + 4 * hl;
+          *reinterpret_cast<float4*>(p.pool + gofs) = ps;                      // global_add_pool, count rows (gnn_model.py:107)
+          const float4 ha = *reinterpret_cast<const float4*>(sCh + i * F + 4 * hl);
+          *reinterpret_cast<float4*>(p.emb_a + gofs) = ha;                     // skip-concat of the canonical row (:275)
           if (l < p.layers) {
-            float2 vt = make_float2(0.f, 0.f), vd = vt;
+            float4 vt = make_float4(0.f, 0.f, 0.f, 0.f), vd = vt;
             const int quirk = sQuirk[i];
             for (int e = sEptr[canon], ee = sEptr[canon + 1]; e < ee; ++e) {
               const int b = edge_at(e);
               const int j = b & 127;
               if (j == quirk) continue;
-              const float2 v = *reinterpret_cast<const float2*>(sStage + j * LDS_ + 2 * lane);
-              if (b & 0x80) add2(vt, v); else add2(vd, v);
+              const float4 v = *reinterpret_cast<const float4*>(sStage + j * LDS_ + 4 * hl);
+              if (b & 0x80) add4(vt, v); else add4(vd, v);
             }
-            *reinterpret_cast<float2*>(sCin + i * NB + 2 * lane) = vt;
-            *reinterpret_cast<float2*>(sCin + i * NB + F + 2 * lane) = vd;
-            *reinterpret_cast<float2*>(sCin + i * NB + 2 * F + 2 * lane) = ha;
+            *reinterpret_cast<float4*>(sCin + i * NB + 4 * hl) = vt;
+            *reinterpret_cast<float4*>(sCin + i * NB + F + 4 * hl) = vd;
+            *reinterpret_cast<float4*>(sCin + i * NB + 2 * F + 4 * hl) = ha;
           }
         }
         if (l == p.layers) break;
-        const uint8_t* wl = p.w_layers + (size_t)l * LAYER_BYTES;
         tc05::fence_proxy_async_smem();  // A images written through the generic proxy -> visible to tcgen05.mma
         __syncthreads();
+        lap(PH_POOL);
 
         // ------------ tensor pipe: P = h . [W_tri | W_tride | W_self]  (one thread issues) ------------
         if (tid == 0) {
@@ -339,72 +369,39 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
           tc05::mma_commit(&bars[1]);
         }
         wphase ^= 1;
+        lap(PH_ISSUE);
 
-        // ------------ CUDA cores meanwhile: canonical rows in fp32 ------------
+        // ------------ CUDA cores meanwhile: canonical rows in fp32 (weights already in registers) ------------
         {
-          const float* WaT = reinterpret_cast<const float*>(wl + OFF_WAT);
-          const float* CwT = reinterpret_cast<const float*>(wl + OFF_CWT);
-          const float* bias_a = reinterpret_cast<const float*>(wl + OFF_BIASA);
-          {  // z_a = [sum_tri | sum_tride | h_a] . Wa : thread = (n, kq), k = 32 kk + 4 kq + {0..3}
-            const int n = tid >> 3, kq = tid & 7;
-            float acc[MAXC];
-#pragma unroll
-            for (int r = 0; r < MAXC; ++r) acc[r] = 0.f;
+          const int n = tid >> 3;   // z_a = [sum_tri | sum_tride | h_a] . Wa : thread = (n, kq), k = 32 kk + 4 kq + {0..3}
+          const int n2 = tid >> 2;  // cvec = h_a . [Cw_tri | Cw_tride]       : thread = (n2, kh), k = 16 kk + 4 kh + {0..3}
+          for (int r = 0; r < nc; ++r) {
+            const float* x = sCin + r * NB;
+            float va = 0.f, vc = 0.f;
 #pragma unroll
             for (int kk = 0; kk < NB / 32; ++kk) {
-              const int k = 32 * kk + 4 * kq;
-              const float4 w = __ldg(reinterpret_cast<const float4*>(WaT + (size_t)n * NB + k));
-#pragma unroll
-              for (int r = 0; r < MAXC; ++r) {
-                if (r < nc) {
-                  const float4 x = *reinterpret_cast<const float4*>(sCin + r * NB + k);
-                  acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
-                }
-              }
+              const float4 xv = *reinterpret_cast<const float4*>(x + 32 * kk + 4 * kq);
+              va = fmaf(xv.x, wa[kk].x, fmaf(xv.y, wa[kk].y, fmaf(xv.z, wa[kk].z, fmaf(xv.w, wa[kk].w, va))));
             }
-            const float b = bias_a[n];
-#pragma unroll
-            for (int r = 0; r < MAXC; ++r) {
-              if (r < nc) {
-                float v = acc[r];
-                v += __shfl_xor_sync(FULL_MASK, v, 1);
-                v += __shfl_xor_sync(FULL_MASK, v, 2);
-                v += __shfl_xor_sync(FULL_MASK, v, 4);
-                if (kq == 0) sCh[r * F + n] = fmaxf(v + b, 0.f);  // h_a^{l+1}; read again only after the next barrier
-              }
-            }
-          }
-          {  // cvec = h_a . [Cw_tri | Cw_tride] : thread = (n, kh), k = 16 kk + 4 kh + {0..3}
-            const int n = tid >> 2, kh = tid & 3;
-            float acc[MAXC];
-#pragma unroll
-            for (int r = 0; r < MAXC; ++r) acc[r] = 0.f;
 #pragma unroll
             for (int kk = 0; kk < F / 16; ++kk) {
-              const int k = 16 * kk + 4 * kh;
-              const float4 w = __ldg(reinterpret_cast<const float4*>(CwT + (size_t)n * F + k));
-#pragma unroll
-              for (int r = 0; r < MAXC; ++r) {
-                if (r < nc) {
-                  const float4 x = *reinterpret_cast<const float4*>(sCin + r * NB + 2 * F + k);
-                  acc[r] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[r]))));
-                }
-              }
+              const float4 xv = *reinterpret_cast<const float4*>(x + 2 * F + 16 * kk + 4 * kh);
+              vc = fmaf(xv.x, wc[kk].x, fmaf(xv.y, wc[kk].y, fmaf(xv.z, wc[kk].z, fmaf(xv.w, wc[kk].w, vc))));
             }
-#pragma unroll
-            for (int r = 0; r < MAXC; ++r) {
-              if (r < nc) {
-                float v = acc[r];
-                v += __shfl_xor_sync(FULL_MASK, v, 1);
-                v += __shfl_xor_sync(FULL_MASK, v, 2);
-                if (kh == 0) sCvec[r * 2 * F + n] = v;
-              }
-            }
+            va += __shfl_xor_sync(FULL_MASK, va, 1);
+            vc += __shfl_xor_sync(FULL_MASK, vc, 1);
+            va += __shfl_xor_sync(FULL_MASK, va, 2);
+            vc += __shfl_xor_sync(FULL_MASK, vc, 2);
+            va += __shfl_xor_sync(FULL_MASK, va, 4);
+            if (kq == 0) sCh[r * F + n] = fmaxf(va + bias_an, 0.f);  // h_a^{l+1}; read again only after the next barrier
+            if (kh == 0) sCvec[r * 2 * F + n2] = vc;
           }
         }
 
+        lap(PH_CANON);
         // ------------ accumulator: TMEM -> shared memory ------------
         if (!tc05::mbar_wait(&bars[1], mphase)) timed_out = true;
+        lap(PH_WAIT_MMA);
         mphase ^= 1;
         tc05::fence_after_sync();
         if (tid == 0) {  // the B images are free again: stream in the next layer's (or the next tile's layer-0) weights
@@ -433,6 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         }
         tc05::fence_before_sync();
         __syncthreads();
+        lap(PH_T2S);
 
         // ------------ segmented, edge-type-split gather out of shared memory; one half-warp per row ------------
         {
@@ -461,7 +459,9 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
           }
         }
         __syncthreads();
+        lap(PH_GATHER);
       }
+      lap(PH_POOL);
       ++tiles_done;
     }
   }
@@ -473,6 +473,18 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
 }
 
 }  // namespace
+
+extern "C" int desco_shmp_fused_phase_cycles(uint64_t* out, int32_t reset) {
+  if (!out) return DESCO_EINVAL;
+  unsigned long long h[PH_COUNT];
+  DESCO_CUDA_TRY(cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof(h)));
+  for (int i = 0; i < PH_COUNT; ++i) out[i] = h[i];
+  if (reset) {
+    for (int i = 0; i < PH_COUNT; ++i) h[i] = 0;
+    DESCO_CUDA_TRY(cudaMemcpyToSymbol(g_phase_cycles, h, sizeof(h)));
+  }
+  return DESCO_OK;
+}
 
 int64_t desco_internal_shmp_fused_workspace_bytes(int num_neighborhoods) {
   const int chunks = (num_neighborhoods + CH - 1) / CH;

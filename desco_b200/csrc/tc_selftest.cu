@@ -15,7 +15,9 @@ constexpr int K = 64;
 __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restrict__ A, const uint8_t* __restrict__ b_image,
                                                           int N, int passes, float* __restrict__ D, int* __restrict__ status) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-B alignment computed as an OFFSET from the __shared__ symbol, so the compiler keeps the shared address space
+  // (LDS/STS); casting through uintptr_t would turn every access into a generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sAhi = smem;
   uint8_t* sAlo = sAhi + M * 128;
   uint8_t* sBhi = sAlo + M * 128;

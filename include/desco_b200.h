@@ -173,6 +173,11 @@ int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_
                          const float* w_gossip_query, float* out, float* out_gates, void* workspace,
                          int64_t workspace_bytes, int32_t precision, void* stream);
 
+/* Phase profile of the fused SHMP layer kernel (measurement support, no reference counterpart): clock64 cycles summed
+ * over all CTAs since the last reset, as seen by thread 0 of each CTA.  out[7] = {tile setup, pool + canonical inputs,
+ * weight wait + MMA issue, canonical rows on the CUDA cores, wait for the MMA, TMEM -> shared memory, gather}. */
+int desco_shmp_fused_phase_cycles(uint64_t* out, int32_t reset);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Tensor-core self test (no reference counterpart): d[128][n] = a[128][64] . B[n][64]^T on tcgen05 with the bf16 hi/lo
  * split (passes = 1: hi.hi only, 3: hi.hi + lo.hi + hi.lo).  b_image is the pre-swizzled operand image built by
