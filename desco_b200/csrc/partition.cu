@@ -330,6 +330,248 @@ __global__ void __launch_bounds__(256) partition_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Small-graph regime (every target graph <= 256 nodes: molecule / ego / protein datasets, configs 1-4).
+// One warp per centre, but the whole target graph is first turned into an adjacency BIT-MATRIX in shared memory
+// (lane-per-node: row u = W words), shared by the consecutive centres a warp processes.  Every set operation of the
+// partition is then a handful of word-wide ANDs/ORs held REPLICATED in registers across the warp:
+//   frontier expansion  next = OR_{u in F} adj[u]      lane-per-node + one __reduce_or_sync per word
+//   <= centre filter    one mask per word;   component of the centre: the same expansion restricted to the mask
+//   SHMP edge type      tri(u,v) = (adj[u] & adj[v] & S) != 0
+//   emission            lane-per-node: local ids by popcount prefix, per-row offsets by a warp scan
+// ------------------------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) partition_small_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ graph_ptr,
+    int num_graphs, const int32_t* __restrict__ centres, int num_centres, int depth, int mode, int run,
+    int32_t* __restrict__ out_nv, int32_t* __restrict__ out_ne, int32_t* __restrict__ centre_graph, int fill,
+    const int32_t* __restrict__ node_off, const int32_t* __restrict__ edge_off, int32_t* __restrict__ node_gid,
+    int32_t* __restrict__ edge_ptr, int32_t* __restrict__ edge_col, uint8_t* __restrict__ edge_tri,
+    int32_t* __restrict__ status) {
+  constexpr int PW = (W == 1) ? 1 : W + 1;  // odd row pitch: lane-per-row reads are bank-conflict free
+  extern __shared__ uint32_t smem[];
+  const int lane = lane_id(), warp = warp_id();
+  uint32_t* adj = smem + (size_t)warp * (32 * W) * PW;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  int cached_gid = -1, lo = 0, hi = 0;
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const int c_begin = (int)min((long long)num_centres, gw * run);
+  const int c_end = (int)min((long long)num_centres, (gw + 1) * run);
+  for (int ci = c_begin; ci < c_end; ++ci) {
+    const int centre = centres[ci];
+    if (fill && out_ne[ci] == 0) continue;  // dropped neighborhood (workload.py:253-256)
+    if (centre < lo || centre >= hi) {      // a different target graph: locate it and rebuild the bit-matrix
+      int gid;
+      if (fill) {
+        gid = centre_graph[ci];
+      } else {  // 32-ary search: largest gid with graph_ptr[gid] <= centre
+        int a = 0, b = num_graphs;
+        while (b - a > 1) {
+          const int step = (b - a + 31) >> 5;
+          const int probe = min(a + lane * step, b);
+          const bool le = probe < b && graph_ptr[probe] <= centre;
+          const int k = __popc(__ballot_sync(FULL_MASK, le)) - 1;  // predicates are monotone in the lane index
+          const int na = a + k * step;
+          b = min(b, na + step);
+          a = na;
+        }
+        gid = a;
+      }
+      cached_gid = gid;
+      lo = graph_ptr[gid];
+      hi = graph_ptr[gid + 1];
+      if (hi - lo > 32 * W) {  // caller promised an upper bound that does not hold
+        if (lane == 0) {
+          atomicExch(status, DESCO_ERANGE);
+          if (!fill) { out_nv[ci] = 0; out_ne[ci] = 0; centre_graph[ci] = gid; }
+        }
+        hi = lo;  // invalidate the cache
+        continue;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const int u = 32 * i + lane;
+        uint32_t row[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) row[j] = 0u;
+        if (lo + u < hi) {
+          for (int e = rowptr[lo + u], ee = rowptr[lo + u + 1]; e < ee; ++e) {
+            const int v = col[e] - lo;
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+              if ((v >> 5) == j) row[j] |= 1u << (v & 31);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) adj[u * PW + j] = row[j];
+      }
+      __syncwarp();
+    }
+    const int gid = cached_gid;
+    const int cl = centre - lo;
+
+    // next = OR of adj[u] over the nodes u of F (lane-per-node), identical in every lane afterwards
+    auto expand = [&](const uint32_t (&Fr)[W], uint32_t (&nx)[W]) {
+      uint32_t acc[W];
+#pragma unroll
+      for (int j = 0; j < W; ++j) acc[j] = 0u;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        if ((Fr[i] >> lane) & 1u) {
+#pragma unroll
+          for (int j = 0; j < W; ++j) acc[j] |= adj[(32 * i + lane) * PW + j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < W; ++j) nx[j] = __reduce_or_sync(FULL_MASK, acc[j]);
+    };
+
+    uint32_t S[W], Fr[W], le[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const uint32_t init = (j == (cl >> 5)) ? (1u << (cl & 31)) : 0u;
+      S[j] = init;
+      Fr[j] = init;
+      le[j] = (mode == DESCO_MODE_KHOP) ? 0xffffffffu
+              : (j < (cl >> 5)) ? 0xffffffffu : (j == (cl >> 5) ? (0xffffffffu >> (31 - (cl & 31))) : 0u);
+    }
+    // phase A: k rounds of frontier expansion (data.py:332-337 unrestricted / :344-349 through nodes <= centre)
+    for (int level = 0; level < depth; ++level) {
+      uint32_t nx[W];
+      expand(Fr, nx);
+      uint32_t any = 0u;
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        uint32_t f = nx[j] & ~S[j];
+        if (mode == DESCO_MODE_CANONICAL) f &= le[j];
+        Fr[j] = f;
+        S[j] |= f;
+        any |= f;
+      }
+      if (!any) break;
+    }
+    if (mode == DESCO_MODE_HETERO) {
+      // phase B: keep candidates <= centre (data.py:385); phase C: component of the centre inside them (:387-390)
+      uint32_t comp[W];
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        S[j] &= le[j];
+        const uint32_t init = (j == (cl >> 5)) ? (1u << (cl & 31)) : 0u;
+        comp[j] = init;
+        Fr[j] = init;
+      }
+      while (true) {
+        uint32_t nx[W];
+        expand(Fr, nx);
+        uint32_t any = 0u;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          const uint32_t f = nx[j] & S[j] & ~comp[j];
+          Fr[j] = f;
+          comp[j] |= f;
+          any |= f;
+        }
+        if (!any) break;
+      }
+#pragma unroll
+      for (int j = 0; j < W; ++j) S[j] = comp[j];
+    }
+    // phase D: popcount prefix -> dense local ids in ascending node order; induced degrees, lane-per-node
+    int pref[W];
+    int nv = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      pref[j] = nv;
+      nv += __popc(S[j]);
+    }
+    uint32_t nb[W][W];  // nb[i] = induced adjacency row of node 32 i + lane
+    int deg[W];
+    int my_edges = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const bool in = (S[i] >> lane) & 1u;
+      deg[i] = 0;
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        nb[i][j] = in ? (adj[(32 * i + lane) * PW + j] & S[j]) : 0u;
+        deg[i] += __popc(nb[i][j]);
+      }
+      my_edges += deg[i];
+    }
+    const int ne = warp_sum(my_edges);
+    if (!fill) {
+      if (lane == 0) {
+        out_ne[ci] = ne;
+        out_nv[ci] = ne > 0 ? nv : 0;
+        centre_graph[ci] = gid;
+      }
+      continue;
+    }
+    // ---- fill pass ----
+    const int n0 = node_off[ci], e0 = edge_off[ci];
+    if (n0 == 0 && lane == 0) edge_ptr[0] = 0;
+    int carry = e0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const int incl = warp_incl_scan(deg[i]);
+      int out = carry + incl - deg[i];
+      carry += __shfl_sync(FULL_MASK, incl, 31);
+      if ((S[i] >> lane) & 1u) {
+        const int u = 32 * i + lane;
+        const int row = n0 + pref[i] + __popc(S[i] & lt_mask);
+        node_gid[row] = lo + u;
+        edge_ptr[row + 1] = out + deg[i];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          uint32_t bits = nb[i][j];
+          while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int v = 32 * j + b;
+            uint32_t common = 0u;  // (A*A^2 + A)[u,v] > 1  <=>  common neighbour inside S (transforms.py:201-221)
+#pragma unroll
+            for (int k = 0; k < W; ++k) common |= nb[i][k] & adj[v * PW + k];
+            edge_col[out] = n0 + pref[j] + __popc(S[j] & ((1u << b) - 1u));
+            edge_tri[out] = common ? 1 : 0;
+            ++out;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int W>
+int launch_partition_small(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int num_graphs,
+                           const int32_t* centres, int num_centres, int depth, int mode, int32_t* nv, int32_t* ne,
+                           int32_t* centre_graph, int fill, const int32_t* node_off, const int32_t* edge_off,
+                           int32_t* node_gid, int32_t* edge_ptr, int32_t* edge_col, uint8_t* edge_tri, int32_t* status,
+                           cudaStream_t stream) {
+  constexpr int PW = (W == 1) ? 1 : W + 1;
+  const int warps = 8, threads = warps * 32;
+  const size_t smem = (size_t)warps * 32 * W * PW * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    DESCO_CUDA_TRY(cudaFuncSetAttribute(partition_small_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int sms = desco_num_sms();
+  // consecutive centres usually share a target graph: a warp keeps its bit-matrix across a short run of them, but
+  // never so long that the grid drops below ~4 warps per scheduler
+  int run = num_centres / (sms * warps * 4);
+  run = run < 1 ? 1 : (run > 8 ? 8 : run);
+  const long long total_warps = ((long long)num_centres + run - 1) / run;
+  const unsigned blocks = (unsigned)((total_warps + warps - 1) / warps);
+  partition_small_kernel<W><<<blocks, threads, smem, stream>>>(rowptr, col, graph_ptr, num_graphs, centres, num_centres,
+                                                              depth, mode, run, nv, ne, centre_graph, fill, node_off,
+                                                              edge_off, node_gid, edge_ptr, edge_col, edge_tri, status);
+  DESCO_LAUNCH_CHECK();
+  return DESCO_OK;
+}
+
 // ToTconvHetero on an existing packed batch: one warp per row, one lane per incident edge.
 __global__ void edge_types_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ edge_col,
                                   int num_rows, uint8_t* __restrict__ edge_tri) {
@@ -387,6 +629,15 @@ int launch_partition(const int32_t* rowptr, const int32_t* col, const int32_t* g
   const int max_words = (max_graph_nodes + 31) / 32;
   const int sms = desco_num_sms();
   DescoProfScope prof(DESCO_PROF_PARTITION, stream);
+#define DESCO_SMALL(Wc)                                                                                                  \
+  return launch_partition_small<Wc>(rowptr, col, graph_ptr, num_graphs, centres, num_centres, depth, mode, nv, ne,       \
+                                    centre_graph, fill, node_off, edge_off, node_gid, edge_ptr, edge_col, edge_tri,      \
+                                    status, stream)
+  if (max_words <= 1) DESCO_SMALL(1);
+  if (max_words <= 2) DESCO_SMALL(2);
+  if (max_words <= 4) DESCO_SMALL(4);
+  if (max_words <= 8) DESCO_SMALL(8);
+#undef DESCO_SMALL
   if (max_words <= 64) {  // warp per centre
     const int threads = 256, groups = threads / 32;
     size_t smem = (size_t)groups * 4 * max_words * sizeof(uint32_t);

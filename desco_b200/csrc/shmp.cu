@@ -410,15 +410,16 @@ int64_t desco_shmp_tc_layer_bytes(void) { return (int64_t)SHMP_TC_LAYER_BYTES; }
 int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
                        int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
                        const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
-                       const void* w_layers_tc, const float* w_readout, int32_t layers, int32_t hidden, float* out_emb,
-                       void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream) {
+                       const void* w_layers_tc, const float* w_readout, const void* w_readout_tc, int32_t layers,
+                       int32_t hidden, float* out_emb, void* workspace, int64_t workspace_bytes, int32_t precision,
+                       int32_t* status, void* stream) {
   const int G = num_neighborhoods, V = num_rows;
   if (hidden != F || layers < 1 || input_dim < 1 || G < 0 || V < 0) return DESCO_EINVAL;
   if (precision < DESCO_PRECISION_FP32 || precision > DESCO_PRECISION_BF16) return DESCO_EINVAL;
   if (G == 0) return DESCO_OK;
   if (!nbh_ptr || !edge_ptr || !edge_col || !edge_tri || !w_pre || !w_readout || !out_emb || !workspace) return DESCO_EINVAL;
   const bool fused = precision != DESCO_PRECISION_FP32;
-  if (fused && (!hetero || !w_layers_tc || !status)) return DESCO_EINVAL;  // tensor-core path: count/canonical batches
+  if (fused && (!hetero || !w_layers_tc || !w_readout_tc || !status)) return DESCO_EINVAL;  // tensor-core path: count/canonical batches
   if (!fused && !w_layers) return DESCO_EINVAL;
   Workspace ws = carve(workspace, V, G, layers);
   if ((int64_t)ws.bytes > workspace_bytes) return DESCO_ENOMEM;
@@ -497,6 +498,22 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
   const float* b3 = r;
   int rc;
   const float* z = ws.pool;
+  if (fused) {  // the same chain on the tensor pipe (csrc/dense_tc.cu); images in w_readout_tc, biases from w_readout
+    const int passes = precision == DESCO_PRECISION_BF16X3 ? 6 : 1;  // the readout sums cancel heavily: full 3-way split
+    const uint8_t* img = (const uint8_t*)w_readout_tc;
+    const uint8_t* iWanc = img; img += (size_t)emb_ld * emb_ld * 6;   // bf16 hi + mid + lo = 6 bytes per weight
+    const uint8_t* iP0 = img; img += (size_t)emb_ld * F * 6;
+    const uint8_t* iP1 = img; img += (size_t)F * F * 6;
+    const uint8_t* iP2 = img; img += (size_t)F * 4 * F * 6;
+    const uint8_t* iP3 = img;
+    if (emb_ld % 96) return DESCO_EINVAL;
+    if ((rc = desco_internal_dense_tc(ws.emb_a, emb_ld, iWanc, banc, ws.pool, emb_ld, ws.z, emb_ld, G, emb_ld, emb_ld, 96, 2, 0.1f, passes, status, s))) return rc;
+    if ((rc = desco_internal_dense_tc(ws.z, emb_ld, iP0, b0, nullptr, 0, ws.t1, F, G, emb_ld, F, 64, 2, 0.1f, passes, status, s))) return rc;
+    if ((rc = desco_internal_dense_tc(ws.t1, F, iP1, b1, nullptr, 0, ws.t2, F, G, F, F, 64, 1, 0.f, passes, status, s))) return rc;
+    if ((rc = desco_internal_dense_tc(ws.t2, F, iP2, b2, nullptr, 0, ws.t3, 4 * F, G, F, 4 * F, 128, 1, 0.f, passes, status, s))) return rc;
+    if ((rc = desco_internal_dense_tc(ws.t3, 4 * F, iP3, b3, nullptr, 0, out_emb, F, G, 4 * F, F, 64, 0, 0.f, passes, status, s))) return rc;
+    return DESCO_OK;
+  }
   if (hetero) {  // z = pool_count + LeakyReLU_0.1(anchor(emb_canonical))  (gnn_model.py:69-73, 88-89, 107)
     rc = dense(ws.emb_a, emb_ld, Wanc, banc, ws.pool, emb_ld, ws.z, emb_ld, G, emb_ld, emb_ld, ACT_LEAKY, 0.1f, s);
     if (rc) return rc;
@@ -515,8 +532,8 @@ int64_t desco_count_head_workspace_bytes(int32_t num_neighborhoods, int32_t num_
 }
 
 int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const float* emb_query, int32_t num_queries,
-                     const float* w_head, int32_t hidden, float* out_pred, float* out_count, void* workspace,
-                     int64_t workspace_bytes, void* stream) {
+                     const float* w_head, const void* w_head_tc, int32_t hidden, float* out_pred, float* out_count,
+                     void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream) {
   const int G = num_neighborhoods, Q = num_queries;
   if (hidden != F || G < 0 || Q < 0) return DESCO_EINVAL;
   if (G == 0 || Q == 0) return DESCO_OK;
@@ -532,8 +549,17 @@ int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const f
   const float* w2 = b1 + HEAD_H;
   const float* b2 = w2 + HEAD_H;
   int rc;
+  if (precision != DESCO_PRECISION_FP32) {
+    if (!w_head_tc || !status) return DESCO_EINVAL;
+    const int passes = precision == DESCO_PRECISION_BF16X3 ? 6 : 1;
+    const uint8_t* iW1a = (const uint8_t*)w_head_tc;
+    const uint8_t* iW1b = iW1a + (size_t)F * HEAD_H * 6;
+    if ((rc = desco_internal_dense_tc(emb_target, F, iW1a, nullptr, nullptr, 0, T, HEAD_H, G, F, HEAD_H, 128, 0, 0.f, passes, status, s))) return rc;
+    if ((rc = desco_internal_dense_tc(emb_query, F, iW1b, b1, nullptr, 0, Bq, HEAD_H, Q, F, HEAD_H, 128, 0, 0.f, passes, status, s))) return rc;
+  } else {
   if ((rc = dense(emb_target, F, W1a, nullptr, nullptr, 0, T, HEAD_H, G, F, HEAD_H, ACT_NONE, 0.f, s))) return rc;
   if ((rc = dense(emb_query, F, W1b, b1, nullptr, 0, Bq, HEAD_H, Q, F, HEAD_H, ACT_NONE, 0.f, s))) return rc;
+  }
   const size_t smem = (size_t)(HEAD_TG * (HEAD_H + 1) + HEAD_H + Q * (HEAD_H + 1)) * sizeof(float);
   if (smem > 200 * 1024) return DESCO_ERANGE;
   DESCO_CUDA_TRY(cudaFuncSetAttribute(count_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

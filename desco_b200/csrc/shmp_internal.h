@@ -20,3 +20,8 @@ int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge
                                      const uint8_t* edge_tri, int G, int pyg_batch_size, const float* feat, int input_dim,
                                      const float* w_pre, const void* w_layers_tc, int layers, int passes, float* emb_a,
                                      float* pool, int emb_ld, void* workspace, int32_t* status, cudaStream_t s);
+
+// Y = act(X . W^T + b) (+ R) on tcgen05 (csrc/dense_tc.cu).  Wimg: pack_dense_tc images; act: 0 none, 1 relu, 2 leaky.
+int desco_internal_dense_tc(const float* X, int ldx, const void* Wimg, const float* bias, const float* R, int ldr, float* Y,
+                            int ldy, int M, int K, int N, int nblk, int act, float slope, int passes, int32_t* status,
+                            cudaStream_t s);

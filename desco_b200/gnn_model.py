@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import _lib
 from .data import NeighborhoodBatch, _ptr, _stream
-from .tcpack import pack_b_operand
+from .tcpack import pack_b_operand, pack_dense_tc
 
 TARGET_META = (
     ["count", "canonical"],
@@ -45,6 +45,42 @@ def _key(et) -> str:
 
 def _params_version(module: nn.Module) -> Tuple:
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+class _PackedWeightsMixin:
+    """Cache of derived (packed / fused) weights.  Validating it exactly - data_ptr and in-place version of every
+    parameter - costs ~100 us of Python per call, more than the kernels it guards.  In pure inference (``eval()`` and
+    autograd disabled) parameters are therefore treated as frozen between the events that can change them behind our
+    back: ``load_state_dict``, ``.to()/.cuda()/.float()`` and ``train()`` bump an epoch that invalidates the cache;
+    in training mode or with autograd enabled the exact check runs every call."""
+
+    def _init_cache(self):
+        self._cache_epoch = 0
+        self._caches = {}
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self._invalidate_caches())
+
+    def _invalidate_caches(self):
+        self._cache_epoch += 1
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._invalidate_caches()
+        return out
+
+    def train(self, mode: bool = True):
+        self._invalidate_caches()
+        return super().train(mode)
+
+    def _cached(self, name: str, module: nn.Module, build):
+        exact = self.training or torch.is_grad_enabled()
+        hit = self._caches.get(name)
+        if hit is not None and hit[0] == self._cache_epoch and not exact:
+            return hit[2]
+        key = _params_version(module)
+        if hit is None or hit[0] != self._cache_epoch or hit[1] != key:
+            hit = (self._cache_epoch, key, build())
+            self._caches[name] = hit
+        return hit[2]
 
 
 class SAGEConv(nn.Module):
@@ -139,12 +175,15 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
     f32 = lambda parts: torch.cat(parts).to(torch.float32).to(dev).contiguous()
     out = {"pre": f32(pre), "layers": f32(layers), "readout": f32(ro)}
     if tc_layers:
+        out["readout_tc"] = torch.cat([pack_dense_tc(d(base.anchor_mlp[0].weight), 96), pack_dense_tc(d(base.post_mp[0].weight), 64),
+                                       pack_dense_tc(d(base.post_mp[3].weight), 64), pack_dense_tc(d(base.post_mp[5].weight), 128),
+                                       pack_dense_tc(d(base.post_mp[7].weight), 64)]).to(dev).contiguous()
         out["layers_tc"] = torch.cat(tc_layers).to(dev).contiguous()
         assert out["layers_tc"].numel() == core.layer_num * _lib.load().desco_shmp_tc_layer_bytes()
     return out
 
 
-class BaseGNN(nn.Module):
+class BaseGNN(_PackedWeightsMixin, nn.Module):
     """``gnn_model.py:18-109`` (SHMP path): ``forward(batch) -> [num_neighborhoods, output_dim]``."""
 
     def __init__(self, input_dim, hidden_dim, output_dim, args, meta=TARGET_META, **kwargs):
@@ -163,14 +202,10 @@ class BaseGNN(nn.Module):
         )
         self.precision = "bf16x3"  # tcgen05 path, ~3e-6 from the fp32 oracle; "fp32" = layer-by-layer FFMA kernels
         self.pyg_batch_size = 0  # 0: the whole NeighborhoodBatch is one collated PyG batch
-        self._packed = None
-        self._packed_version = None
+        self._init_cache()
 
     def packed_weights(self) -> Dict[str, torch.Tensor]:
-        v = _params_version(self)
-        if self._packed is None or v != self._packed_version:
-            self._packed, self._packed_version = pack_shmp_weights(self), v
-        return self._packed
+        return self._cached("packed", self, lambda: pack_shmp_weights(self))
 
     def forward(self, data: NeighborhoodBatch, query_emb=None, feat: Optional[torch.Tensor] = None) -> torch.Tensor:
         if not isinstance(data, NeighborhoodBatch):
@@ -205,8 +240,8 @@ class BaseGNN(nn.Module):
             _lib.check(lib.desco_shmp_forward(
                 _ptr(data.nbh_ptr), _ptr(data.edge_ptr), _ptr(data.edge_col), _ptr(data.edge_tri), G, V, int(hetero),
                 int(self.pyg_batch_size), _ptr(feat), core.input_dim, _ptr(w["pre"]), _ptr(w["layers"]),
-                _ptr(w.get("layers_tc")), _ptr(w["readout"]), core.layer_num, core.hidden_dim, _ptr(out), _ptr(work),
-                wbytes, precision, _ptr(status), _stream()), "desco_shmp_forward")
+                _ptr(w.get("layers_tc")), _ptr(w["readout"]), _ptr(w.get("readout_tc")), core.layer_num, core.hidden_dim,
+                _ptr(out), _ptr(work), wbytes, precision, _ptr(status), _stream()), "desco_shmp_forward")
         if status is not None:
             self.last_status = status  # device int32; 0 = ok.  Checked lazily (check_status) to keep the launch async.
         return out
@@ -295,7 +330,7 @@ def pack_gossip_weights(base: "GossipBaseGNN") -> Dict[str, torch.Tensor]:
     return out
 
 
-class GossipBaseGNN(nn.Module):
+class GossipBaseGNN(_PackedWeightsMixin, nn.Module):
     """``BaseGNN`` with ``baseline="gossip"`` (``gnn_model.py:18-109``): per-node output, no pooling, no anchor."""
 
     def __init__(self, input_dim, hidden_dim, output_dim, args, **kwargs):
@@ -310,14 +345,10 @@ class GossipBaseGNN(nn.Module):
             nn.ReLU(), nn.Linear(hidden_dim, 256), nn.ReLU(), nn.Linear(256, output_dim),
         )
         self.precision = "fp32"
-        self._packed = None
-        self._packed_version = None
+        self._init_cache()
 
     def packed_weights(self):
-        v = _params_version(self)
-        if self._packed is None or v != self._packed_version:
-            self._packed, self._packed_version = pack_gossip_weights(self), v
-        return self._packed
+        return self._cached("packed", self, lambda: pack_gossip_weights(self))
 
     def forward_all_queries(self, rowptr, col, x, query_emb, want_gates=False):
         """out[N,Q] = x + gossip correction for every query column at once."""

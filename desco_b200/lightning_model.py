@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import _lib
 from .data import NeighborhoodBatch, _ptr, _stream, shmp_edge_types
-from .gnn_model import QUERY_META, TARGET_META, BaseGNN, GossipBaseGNN
+from .gnn_model import PRECISION, QUERY_META, TARGET_META, BaseGNN, GossipBaseGNN, _PackedWeightsMixin
 
 STANDARD_QUERY_IDS = [6, 7, 13, 14, 15, 16, 17, 18, 29, 30, 31, 34, 35, 36, 37, 38, 40, 41, 42, 43, 44, 45, 46, 47,
                       48, 49, 50, 51, 52]  # gen_query_ids([3,4,5]), data.py:37-58
@@ -66,7 +66,15 @@ def pack_head_weights(count_model: nn.Sequential, hidden: int) -> torch.Tensor:
     return torch.cat(parts).to(torch.float32).to(count_model[0].weight.device).contiguous()
 
 
-class NeighborhoodCountingModel(nn.Module):
+def pack_head_weights_tc(count_model: nn.Sequential, hidden: int) -> torch.Tensor:
+    """Tensor-core operand images of the two halves of count_model[0] (csrc/dense_tc.cu)."""
+    from .tcpack import pack_dense_tc
+
+    W1 = count_model[0].weight.detach().to("cpu", torch.float64)  # [4h, 2h]
+    return torch.cat([pack_dense_tc(W1[:, :hidden], 128), pack_dense_tc(W1[:, hidden:], 128)]).to(count_model[0].weight.device)
+
+
+class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
     def __init__(self, input_dim=1, hidden_dim=64, args=None, **kwargs):
         super().__init__()
         args = args or default_neighborhood_args(hidden_dim=hidden_dim, input_dim=input_dim)
@@ -79,9 +87,7 @@ class NeighborhoodCountingModel(nn.Module):
         self.emb_model = BaseGNN(input_dim, hidden_dim, hidden_dim, args, TARGET_META, emb_channels=hidden_dim, **kwargs)
         self.emb_model_query = BaseGNN(input_dim, hidden_dim, hidden_dim, args, QUERY_META, emb_channels=hidden_dim, **kwargs)
         self.count_model = nn.Sequential(nn.Linear(2 * hidden_dim, 4 * hidden_dim), nn.LeakyReLU(), nn.Linear(4 * hidden_dim, 1))
-        self._head = None
-        self._head_version = None
-        self._query_emb_cache = None
+        self._init_cache()
 
     # ---- the reference converts with pyg.nn.to_hetero at run time; these modules are built hetero ----
     def to_hetero_old(self, tconv_target=False, tconv_query=False):
@@ -121,25 +127,19 @@ class NeighborhoodCountingModel(nn.Module):
         if getattr(self, "depth", 4) < min_len:  # lightning_model.py:302-308
             warnings.warn("neighborhood diameter {:d} is too small for the queries, the minimum is {:d}".format(self.depth, min_len))
         self.query_loader = batch
-        self._query_emb_cache = None
+        self._invalidate_caches()
 
     def get_query_emb(self) -> torch.Tensor:
         if self.query_loader is None:
             raise RuntimeError("call set_queries first")
-        v = tuple((p.data_ptr(), p._version) for p in self.emb_model_query.parameters())
-        if self._query_emb_cache is None or self._query_emb_cache[0] != v:
-            self._query_emb_cache = (v, self.emb_model_query(self.query_loader))
-        return self._query_emb_cache[1]
+        return self._cached("query_emb", self.emb_model_query, lambda: self.emb_model_query(self.query_loader))
 
     # ---- forward ----
     def graph_to_embed(self, batch) -> torch.Tensor:
         return self.emb_model(batch)
 
     def _head_weights(self):
-        v = tuple((p.data_ptr(), p._version) for p in self.count_model.parameters())
-        if self._head is None or v != self._head_version:
-            self._head, self._head_version = pack_head_weights(self.count_model, self.hidden_dim), v
-        return self._head
+        return self._cached("head", self.count_model, lambda: pack_head_weights(self.count_model, self.hidden_dim))
 
     def embed_to_count(self, embs, want_pred=False):
         """``lightning_model.py:176-193`` for ALL queries at once: embs = (emb_targets [G,h], emb_queries [Q,h])."""
@@ -152,10 +152,15 @@ class NeighborhoodCountingModel(nn.Module):
         wb = int(lib.desco_count_head_workspace_bytes(G, Q))
         work = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
         w = self._head_weights()
+        precision = PRECISION[self.emb_model.precision]
+        w_tc = self._cached("head_tc", self.count_model, lambda: pack_head_weights_tc(self.count_model, self.hidden_dim)) if precision else None
+        status = getattr(self.emb_model, "last_status", None) if precision else None
+        if precision and status is None:
+            status = self.emb_model.last_status = torch.zeros(1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.desco_count_head(_ptr(emb_t), G, _ptr(emb_q), Q, _ptr(w), self.hidden_dim,
-                                            _ptr(out[1]) if want_pred else 0, _ptr(out[0]), _ptr(work), wb, _stream()),
-                       "desco_count_head")
+            _lib.check(lib.desco_count_head(_ptr(emb_t), G, _ptr(emb_q), Q, _ptr(w), _ptr(w_tc), self.hidden_dim,
+                                            _ptr(out[1]) if want_pred else 0, _ptr(out[0]), _ptr(work), wb, precision,
+                                            _ptr(status), _stream()), "desco_count_head")
         return (out[0], out[1]) if want_pred else out[0]
 
     def graph_to_count(self, batch) -> torch.Tensor:

@@ -35,3 +35,27 @@ def pack_b_operand(w: torch.Tensor) -> torch.Tensor:
     """W[n, 64] -> uint8 image: hi rows (n*128 bytes) then lo rows (n*128 bytes)."""
     hi, lo = split_bf16(w.detach().cpu())
     return torch.cat([swizzle_rows(hi), swizzle_rows(lo)])
+
+
+def split_bf16_3(w: torch.Tensor):
+    """fp32 -> (hi, mid, lo) bf16 with hi + mid + lo == w exactly for normal fp32 values (3 x 8 significant bits)."""
+    w32 = w.to(torch.float32)
+    hi = w32.to(torch.bfloat16)
+    r1 = w32 - hi.to(torch.float32)
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.to(torch.float32)).to(torch.bfloat16)
+    return hi, mid, lo
+
+
+def pack_dense_tc(w: torch.Tensor, nblk: int) -> torch.Tensor:
+    """nn.Linear weight W[N, K] -> images for csrc/dense_tc.cu: [column block of nblk][64-wide K atom][hi | mid | lo],
+    each image nblk * 128 bytes (3-way bf16 split: the dense kernel runs up to 6 passes = fp32-grade products)."""
+    w = w.detach().cpu()
+    n, k = w.shape
+    assert n % nblk == 0 and k % 64 == 0, (n, k, nblk)
+    parts = []
+    for nb in range(n // nblk):
+        for a in range(k // 64):
+            blk = w[nb * nblk:(nb + 1) * nblk, a * 64:(a + 1) * 64]
+            parts += [swizzle_rows(x) for x in split_bf16_3(blk)]
+    return torch.cat(parts)

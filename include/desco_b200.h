@@ -119,6 +119,10 @@ int desco_shmp_edge_types(const int32_t* edge_ptr, const int32_t* edge_col, int3
  *             bf16 hi / lo and pre-swizzled (SWIZZLE_128B shared-memory images, desco_b200.tcpack), then fp32
  *             bias_c[64], bias_a[64], Wa^T[64][192], Cw^T[128][64].  May be NULL for precision FP32 (then w_layers is
  *             required); w_layers may be NULL for the tensor-core precisions.
+ *   w_readout_tc  tensor-core form of the readout weights (biases still come from w_readout): operand images of Wanc
+ *             (6 column blocks of 96), P0, P1, P2 (2 blocks of 128), P3 in that order, each
+ *             [column block][64-wide K atom][hi | mid | lo] (3-way bf16 split, 6 tensor-core passes = fp32-grade
+ *             products) as built by desco_b200.tcpack.pack_dense_tc.
  * out_emb: [num_neighborhoods, 64].  precision: DESCO_PRECISION_*.
  * status (device int32, caller-zeroed; required for the tensor-core precisions): DESCO_ERANGE when a neighborhood has
  * more than 128 rows - the fused kernel keeps a whole neighborhood in one 128-row tile - and the caller must rerun
@@ -130,8 +134,9 @@ int64_t desco_shmp_tc_layer_bytes(void);
 int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
                        int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
                        const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
-                       const void* w_layers_tc, const float* w_readout, int32_t layers, int32_t hidden, float* out_emb,
-                       void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream);
+                       const void* w_layers_tc, const float* w_readout, const void* w_readout_tc, int32_t layers,
+                       int32_t hidden, float* out_emb, void* workspace, int64_t workspace_bytes, int32_t precision,
+                       int32_t* status, void* stream);
 
 /* Query-conditioned count head.  Replaces embed_to_count / the per-query loop of graph_to_count
  * (lightning_model.py:176-222, count_model :127-131):  pred[g,q] = count_model(cat(emb_target[g], emb_query[q])),
@@ -139,8 +144,8 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
  * w2[256], b2[1].  out_pred / out_count: [G, Q], either may be NULL. */
 int64_t desco_count_head_workspace_bytes(int32_t num_neighborhoods, int32_t num_queries);
 int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const float* emb_query, int32_t num_queries,
-                     const float* w_head, int32_t hidden, float* out_pred, float* out_count, void* workspace,
-                     int64_t workspace_bytes, void* stream);
+                     const float* w_head, const void* w_head_tc, int32_t hidden, float* out_pred, float* out_count,
+                     void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Gossip propagation (forward)
