@@ -67,17 +67,31 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
   };
   if (tid == 0) issue_b(0);
 
+  constexpr int ROWS_PER_THREAD = TM / (THREADS / 16);  // 8 row slices (float4) per thread and atom
+  float4 xin[ROWS_PER_THREAD], xnext[ROWS_PER_THREAD];
+  auto load_x = [&](int a, float4 (&dst)[ROWS_PER_THREAD]) {
+#pragma unroll
+    for (int it = 0; it < ROWS_PER_THREAD; ++it) {
+      const int r = warp * 2 + hw + it * (THREADS / 16);
+      dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < p.M) dst[it] = __ldg(reinterpret_cast<const float4*>(p.X + (size_t)(m0 + r) * p.ldx + 64 * a + 4 * hl));
+    }
+  };
+  load_x(0, xin);
+
   for (int a = 0; a < KA; ++a) {
     const int s = a & 1;
     if (a + 1 < KA) {  // free the other stage (read by the MMAs of atom a-1) and start fetching atom a+1's weights
+      load_x(a + 1, xnext);  // ... and atom a+1 of X: in flight while atom a is converted and multiplied
       if (a >= 1 && !tc05::mbar_wait(&bars[2 + (s ^ 1)], ((a - 1) >> 1) & 1)) timed_out = true;
       if (tid == 0) issue_b(a + 1);
     }
-    // X[m0 .. m0+127][64 a .. 64 a + 63] -> bf16 hi / lo swizzled images (one half-warp per row)
+    // X[m0 .. m0+127][64 a .. 64 a + 63] -> bf16 hi / mid / lo swizzled images (one half-warp per row)
     uint8_t* sA = stage_ptr(s);  // hi | mid | lo images of the A atom, then hi | mid | lo of the B atom
-    for (int r = warp * 2 + hw; r < TM; r += THREADS / 16) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + r < p.M) v = *reinterpret_cast<const float4*>(p.X + (size_t)(m0 + r) * p.ldx + 64 * a + 4 * hl);
+#pragma unroll
+    for (int it = 0; it < ROWS_PER_THREAD; ++it) {
+      const int r = warp * 2 + hw + it * (THREADS / 16);
+      const float4 v = xin[it];
       const float x[4] = {v.x, v.y, v.z, v.w};
       __align__(8) __nv_bfloat16 hi[4], mid[4], lo[4];
 #pragma unroll
@@ -92,6 +106,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
       *reinterpret_cast<uint2*>(sA + A_BYTES + off) = *reinterpret_cast<const uint2*>(mid);
       *reinterpret_cast<uint2*>(sA + 2 * A_BYTES + off) = *reinterpret_cast<const uint2*>(lo);
     }
+#pragma unroll
+    for (int it = 0; it < ROWS_PER_THREAD; ++it) xin[it] = xnext[it];
     tc05::fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {

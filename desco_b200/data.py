@@ -118,6 +118,18 @@ class NeighborhoodBatch:
         gid = np.searchsorted(gp, c, side="right") - 1
         return np.stack([gid, c - gp[gid]], axis=1)
 
+    def slice(self, g0: int, g1: int) -> "NeighborhoodBatch":
+        """Neighborhoods [g0, g1) as their own packed batch (what one DataLoader step of ``batch_size`` consecutive
+        neighborhoods would collate, ``lightning_data.py:78-100``).  Needs the two offsets on the host: one small sync."""
+        g1 = min(g1, self.num_neighborhoods)
+        r0, r1 = (int(x) for x in self.nbh_ptr[[g0, g1]].cpu())
+        e0, e1 = (int(x) for x in self.edge_ptr[[r0, r1]].cpu())
+        return NeighborhoodBatch(
+            self.nbh_ptr[g0:g1 + 1] - r0, self.node_gid[r0:r1], self.edge_ptr[r0:r1 + 1] - e0, self.edge_col[e0:e1] - r0,
+            self.edge_tri[e0:e1], self.centre[g0:g1], None, None, self.graph_ptr, g1 - g0, r1 - r0, e1 - e0,
+            hetero=self.hetero, max_rows=self.max_rows,
+        )
+
     @staticmethod
     def from_numpy(d: Dict[str, np.ndarray], device=None, hetero: bool = True) -> "NeighborhoodBatch":
         dev = _require_cuda(device)

@@ -369,3 +369,35 @@ class GossipBaseGNN(_PackedWeightsMixin, nn.Module):
                                                 _ptr(w["wq"]), _ptr(out), _ptr(gates), _ptr(work), wb,
                                                 PRECISION[self.precision], _stream()), "desco_gossip_forward")
         return (out, gates) if want_gates else out
+
+
+def _gossip_forward_node_range(self, rowptr, col, x, query_emb, node_begin, node_end, exchange):
+    """Node-range shard of the gossip forward (desco_b200.distributed): layer 0 for [node_begin, node_end) from the
+    replicated counts ``x[N,Q]``, ``exchange`` (all-gather of row blocks) of the layer-0 scalars s4 - the halo - then
+    layer 1 + post_mp for the same range and a final exchange of the output rows.  Returns out[N,Q]."""
+    if self.training:
+        raise NotImplementedError("gossip training is not a CUDA path yet")
+    lib = _lib.load()
+    w = self.packed_weights()
+    dev = w["wg"].device
+    x = x.to(device=dev, dtype=torch.float32).contiguous()
+    query_emb = query_emb.to(device=dev, dtype=torch.float32).contiguous()
+    N, Q = x.shape
+    n_loc = node_end - node_begin
+    qvec = torch.empty((Q, 256), dtype=torch.float32, device=dev)
+    s4_full_local = torch.zeros((N, Q, 4), dtype=torch.float32, device=dev) if n_loc else torch.zeros((0, Q, 4), device=dev)
+    with torch.cuda.device(dev):
+        st = _stream()
+        _lib.check(lib.desco_gossip_prepare_queries(_ptr(query_emb), Q, _ptr(w["wq"]), _ptr(qvec), 0, st), "gossip_prepare_queries")
+        if n_loc:
+            _lib.check(lib.desco_gossip_layer0(_ptr(rowptr), _ptr(col), node_begin, node_end, _ptr(x), Q, _ptr(qvec),
+                                               _ptr(s4_full_local), st), "gossip_layer0")
+        s4 = exchange(s4_full_local[node_begin:node_end].contiguous()).contiguous()  # halo exchange -> s4[N,Q,4] everywhere
+        out_full = torch.zeros((N, Q), dtype=torch.float32, device=dev)
+        if n_loc:
+            _lib.check(lib.desco_gossip_layer1(_ptr(rowptr), _ptr(col), node_begin, node_end, _ptr(s4), Q, _ptr(qvec),
+                                               _ptr(w["wg"]), _ptr(out_full), PRECISION[self.precision], st), "gossip_layer1")
+    return exchange(out_full[node_begin:node_end].contiguous())
+
+
+GossipBaseGNN.forward_node_range = _gossip_forward_node_range

@@ -1,0 +1,126 @@
+"""GPU: the counting driver end to end (Workload -> canonical partition -> SHMP counts -> gossip -> graph-level sums)
+against the same sequence run through the oracle, on the MUTAG-shaped config (BASELINE.json configs[0])."""
+import numpy as np
+import pytest
+import torch
+
+from desco_b200.graph import gen_mutag_shaped
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a - b).abs() / b.abs().clamp(min=1.0)).max().item()
+
+
+def _models(seed):
+    from desco_b200.lightning_model import GossipCountingModel, NeighborhoodCountingModel, STANDARD_QUERY_IDS
+    from oracle import model as M
+
+    torch.manual_seed(seed)
+    om, og = M.NeighborhoodCountingModel().eval(), M.GossipCountingModel()
+    pm, pg = NeighborhoodCountingModel().eval(), GossipCountingModel()
+    pm.load_state_dict(om.state_dict())
+    pg.emb_model.load_state_dict(og.emb_model.state_dict())
+    pm, pg = pm.cuda(), pg.cuda()
+    pm.set_queries(STANDARD_QUERY_IDS)
+    return om, og, pm, pg
+
+
+def test_pipeline_matches_oracle_mutag_shaped(cuda_device, tmp_path):
+    from desco_b200.workload import Workload, count_subgraphs
+    from oracle import model as M
+    from oracle import partition as P
+
+    csr = gen_mutag_shaped(seed=0, num_graphs=60)
+    om, og, pm, pg = _models(3)
+    # ---- oracle: workload.py:250-260 loop, lightning_model.py:198-222, workload.py:107-112, :613-628, :136-148 ----
+    b = P.partition_dataset(csr, 4)
+    qb = M.query_batch()
+    with torch.no_grad():
+        ref_counts = om.graph_to_count(b, qb, pyg_batch_size=512)
+        x = torch.zeros(csr.num_nodes, ref_counts.shape[1])
+        x[torch.as_tensor(b["indicator"])] = ref_counts
+        og.set_query_emb(om.get_query_emb(qb))
+        ref_nodes = og.graph_to_count(x, torch.from_numpy(csr.edge_index()))
+    gid = torch.as_tensor(csr.graph_of(np.arange(csr.num_nodes)))
+    ref_graph = torch.zeros(csr.num_graphs, x.shape[1]).index_add_(0, gid, ref_nodes)
+    # ---- product ----
+    wl = Workload(csr, str(tmp_path))
+    counts, nodes, graphs = count_subgraphs(wl, pm, pg, depth=4, batch_size=512)
+    torch.cuda.synchronize()
+    pm.emb_model.check_status()
+    nd = wl.neighborhood_dataset
+    assert np.array_equal(nd.nx_neighs_index, b["index"]) and np.array_equal(nd.nx_neighs_indicator, b["indicator"])
+    assert (tmp_path / "NeighborhoodDataset" / "processed" / "neighs_index_depth_4.npy").exists()
+    assert _rel(counts.cpu(), ref_counts) <= 1e-4
+    assert _rel(nodes.cpu(), ref_nodes) <= 1e-4
+    assert graphs.shape == (60, 29) and _rel(graphs.cpu(), ref_graph) <= 1e-4
+    # neighborhood-level aggregation (workload.py:303-324)
+    agg = nd.aggregate_neighborhood_count(counts)
+    ref_agg = torch.zeros(60, 29).index_add_(0, torch.as_tensor(b["index"][:, 0]), ref_counts)
+    assert _rel(agg, ref_agg) <= 1e-4
+
+
+def test_loader_batches_equal_whole_dataset(cuda_device):
+    """DataLoader-style chunks of 512 neighborhoods (config.py:255) give the same counts as the one-pass batch when the
+    reference quirk is evaluated per chunk either way."""
+    from desco_b200.workload import Workload
+
+    _, _, pm, _ = _models(4)
+    wl = Workload(gen_mutag_shaped(seed=1, num_graphs=80), None)
+    wl.generate_pipeline_datasets(depth_neigh=4)
+    nd = wl.neighborhood_dataset
+    pm.set_pyg_batch_size(512)
+    with torch.no_grad():
+        whole = pm.graph_to_count(nd.batch)
+        parts = torch.cat([pm.graph_to_count(bt) for bt in nd.loader(512)], 0)
+    assert len(nd) > 512 and parts.shape == whole.shape
+    assert (parts - whole).abs().max().item() <= 1e-6
+
+
+def test_sharded_pipeline_single_rank_equals_direct(cuda_device):
+    """distributed.ShardedPipeline with world size 1 (no process group): same numbers as the direct calls, and the
+    node-range gossip entry with several ranges stitched by hand equals the single call."""
+    from types import SimpleNamespace
+
+    from desco_b200.data import DeviceCSR, partition_batch
+    from desco_b200.distributed import ShardedPipeline, node_ranges
+
+    _, _, pm, pg = _models(5)
+    csr = gen_mutag_shaped(seed=2, num_graphs=40)
+    g = DeviceCSR.from_host(csr)
+    sp = ShardedPipeline(g, pm, pg, depth=4)
+    centres, counts = sp.count_neighborhoods()
+    with torch.no_grad():
+        direct = pm.graph_to_count(partition_batch(g, None, 4))
+    assert torch.equal(counts, direct)
+    x = sp.gather_node_counts(centres, counts)
+    qe = pm.get_query_emb()
+    out = sp.gossip(x, qe)
+    pg.set_query_emb(qe)
+    with torch.no_grad():
+        ref = pg.graph_to_count(SimpleNamespace(graph=g, x=x))
+    assert torch.equal(out, ref)
+    # three "ranks" emulated in one process: each computes its node range; the exchange stitches the blocks
+    N = g.num_nodes
+    ranges = node_ranges(N, 3)
+    s4_blocks, out_blocks = {}, {}
+
+    def run(rank, stage_store):
+        lo, hi = ranges[rank]
+        calls = []
+
+        def exchange(t):
+            calls.append(t)
+            if len(calls) == 1:  # halo scalars: use the blocks every rank computed in the first sweep
+                return torch.cat([stage_store[r] for r in range(3)], 0) if len(stage_store) == 3 else torch.zeros(N, *t.shape[1:], device=t.device).index_copy_(0, torch.arange(lo, hi, device=t.device), t)
+            return t
+        res = pg.emb_model.forward_node_range(g.rowptr, g.col, x, qe, lo, hi, exchange)
+        return calls[0], res
+
+    for r in range(3):  # sweep 1: collect every rank's s4 block
+        s4_blocks[r], _ = run(r, {})
+    for r in range(3):  # sweep 2: with the full halo available
+        _, out_blocks[r] = run(r, s4_blocks)
+    assert torch.equal(torch.cat([out_blocks[r] for r in range(3)], 0), ref)
