@@ -10,8 +10,9 @@ SHMP forward (8 fused layers + readout) -> query-conditioned count head, for the
 Python API from pinned HOST buffers (CSR + centres copied H2D, counts copied D2H inside the timed region).
 
 Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write) between steps and excluded;
-max over ranks.  Roofline: the dominant kernel (shmp_layer_kernel) timed live by the library's own CUDA-event hooks
-(include/desco_b200.h desco_profile_*), algorithmic bytes per launch = 4F(E + 2V).
+max over ranks.  Roofline: the dominant kernel (shmp_fused_kernel, all 8 layers in one launch) timed live by the
+library's own CUDA-event hooks (include/desco_b200.h desco_profile_*), algorithmic bytes per launch = 8 * 4F(E + 2V)
+(SURVEY.md section 8d).
 """
 from __future__ import annotations
 
@@ -265,12 +266,14 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = _peaks()
         layer_ms, layer_launches = prof[0][1], prof[1][1]
-        alg_bytes = 4 * 64 * (E + 2 * V)  # per layer launch: gather E rows, read V self rows, write V rows (fp32 x 64)
+        # one fused launch runs all 8 layers; per layer the reference formulation gathers E rows, reads V self rows and
+        # writes V rows (fp32 x 64): B_shmp = L * 4F * (E + 2V)   
+        alg_bytes = 8 * 4 * 64 * (E + 2 * V)
         achieved = alg_bytes / (layer_ms / max(layer_launches, 1) * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("shmp_layer_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("shmp_fused_kernel_dram_bytes_per_launch")
         # bounded CPU baseline (oracle port) on this box's host cores
         om, qb = cpu_models()
         t0 = time.perf_counter()
@@ -283,12 +286,12 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "depth": DEPTH, "queries": 29, "neighborhoods_per_gpu": G, "rows": V,
                        "directed_edges": E, "pyg_batch_size": 512, "l2": "flushed between steps (256 MiB write)",
-                       "precision": "fp32 FFMA"},
+                       "precision": "bf16x3 tcgen05 layers + bf16x6 readout, fp32 accumulate (1e-4 parity path)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "shmp_layer_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "shmp_fused_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": layer_ms / max(layer_launches, 1),
                          "launches_timed": int(layer_launches)},
