@@ -508,11 +508,7 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
     const uint8_t* iP3 = img;
     if (emb_ld % 96) return DESCO_EINVAL;
     if ((rc = desco_internal_dense_tc(ws.emb_a, emb_ld, iWanc, banc, ws.pool, emb_ld, ws.z, emb_ld, G, emb_ld, emb_ld, 96, 2, 0.1f, passes, status, s))) return rc;
-    if ((rc = desco_internal_dense_tc(ws.z, emb_ld, iP0, b0, nullptr, 0, ws.t1, F, G, emb_ld, F, 64, 2, 0.1f, passes, status, s))) return rc;
-    if ((rc = desco_internal_dense_tc(ws.t1, F, iP1, b1, nullptr, 0, ws.t2, F, G, F, F, 64, 1, 0.f, passes, status, s))) return rc;
-    if ((rc = desco_internal_dense_tc(ws.t2, F, iP2, b2, nullptr, 0, ws.t3, 4 * F, G, F, 4 * F, 128, 1, 0.f, passes, status, s))) return rc;
-    if ((rc = desco_internal_dense_tc(ws.t3, 4 * F, iP3, b3, nullptr, 0, out_emb, F, G, 4 * F, F, 64, 0, 0.f, passes, status, s))) return rc;
-    return DESCO_OK;
+    return desco_internal_readout_chain(ws.z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, s);
   }
   if (hetero) {  // z = pool_count + LeakyReLU_0.1(anchor(emb_canonical))  (gnn_model.py:69-73, 88-89, 107)
     rc = dense(ws.emb_a, emb_ld, Wanc, banc, ws.pool, emb_ld, ws.z, emb_ld, G, emb_ld, emb_ld, ACT_LEAKY, 0.1f, s);
@@ -520,11 +516,7 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
     z = ws.z;
   }
   // post_mp (gnn_model.py:44-53)
-  if ((rc = dense(z, emb_ld, P0, b0, nullptr, 0, ws.t1, F, G, emb_ld, F, ACT_LEAKY, 0.1f, s))) return rc;
-  if ((rc = dense(ws.t1, F, P1, b1, nullptr, 0, ws.t2, F, G, F, F, ACT_RELU, 0.f, s))) return rc;
-  if ((rc = dense(ws.t2, F, P2, b2, nullptr, 0, ws.t3, 4 * F, G, F, 4 * F, ACT_RELU, 0.f, s))) return rc;
-  if ((rc = dense(ws.t3, 4 * F, P3, b3, nullptr, 0, out_emb, F, G, 4 * F, F, ACT_NONE, 0.f, s))) return rc;
-  return DESCO_OK;
+  return desco_internal_readout_chain(z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, s);
 }
 
 int64_t desco_count_head_workspace_bytes(int32_t num_neighborhoods, int32_t num_queries) {
@@ -548,6 +540,8 @@ int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const f
   const float* b1 = W1b + F * HEAD_H;
   const float* w2 = b1 + HEAD_H;
   const float* b2 = w2 + HEAD_H;
+  if (Q <= 32)  // one fused launch (csrc/readout.cu); the multi-launch path below serves larger query sets
+    return desco_internal_count_head_fused(emb_target, G, emb_query, Q, W1a, W1b, b1, w2, b2, out_pred, out_count, s);
   int rc;
   if (precision != DESCO_PRECISION_FP32) {
     if (!w_head_tc || !status) return DESCO_EINVAL;

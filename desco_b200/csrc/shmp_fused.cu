@@ -31,6 +31,7 @@ constexpr int MAXC = SHMP_TILE_MAX_NBH; // neighborhoods per tile
 constexpr int NB = 3 * F;               // GEMM N: [tri | tride | self]
 constexpr int THREADS = 512;
 constexpr int NWARPS = THREADS / 32;
+constexpr int ISSUER = THREADS - 32;      // thread that talks to the tensor pipe / TMA engine (lane 0 of the last warp)
 constexpr int LDP = 2 * F + 4;          // row pitch (floats) of the P_tri|P_tride buffer
 constexpr int LDS_ = F + 4;             // row pitch (floats) of the fp32 staging rows (P_self, then h')
 constexpr int EDGE_CAP = 8192;          // staged edges per tile (1 byte each); larger tiles read edges from global
@@ -190,11 +191,11 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
   tc05::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t layer_image_bytes = 2 * NB * 128;
-  if (tid == 0) {  // weights of layer 0 for the first tile
+  if (tid == ISSUER) {  // weights of layer 0 for the first tile
     tc05::mbar_arrive_expect_tx(&bars[0], layer_image_bytes);
     tc05::bulk_g2s(sBhi, p.w_layers + OFF_BHI, layer_image_bytes, &bars[0]);
   }
-  bool copy_pending = true;  // meaningful in thread 0 only
+  bool copy_pending = true;  // meaningful in the ISSUER thread only
   uint32_t wphase = 0, mphase = 0;
   int tiles_done = 0;
   bool timed_out = false;
@@ -301,56 +302,14 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
           }
         }
       }
+      tc05::fence_proxy_async_smem();  // A images written through the generic proxy -> visible to tcgen05.mma
       __syncthreads();
       lap(PH_SETUP);
 
       for (int l = 0; l <= p.layers; ++l) {
-        // this thread's slice of the canonical-row weights of layer l: issued now, consumed after the pool phase
-        const uint8_t* wl = p.w_layers + (size_t)(l < p.layers ? l : 0) * LAYER_BYTES;
-        const int kq = tid & 7, kh = tid & 3;
-        float4 wa[NB / 32], wc[F / 16];
-        float bias_an = 0.f;
-        if (l < p.layers) {
-          const float* WaT = reinterpret_cast<const float*>(wl + OFF_WAT) + (size_t)(tid >> 3) * NB + 4 * kq;
-          const float* CwT = reinterpret_cast<const float*>(wl + OFF_CWT) + (size_t)(tid >> 2) * F + 4 * kh;
-#pragma unroll
-          for (int kk = 0; kk < NB / 32; ++kk) wa[kk] = __ldg(reinterpret_cast<const float4*>(WaT + 32 * kk));
-#pragma unroll
-          for (int kk = 0; kk < F / 16; ++kk) wc[kk] = __ldg(reinterpret_cast<const float4*>(CwT + 16 * kk));
-          bias_an = __ldg(reinterpret_cast<const float*>(wl + OFF_BIASA) + (tid >> 3));
-        }
-        // ------------ pool + canonical inputs of layer l (from the fp32 rows of h^l in sStage, h_a^l in sCh) ------------
-        for (int i = warp * 2 + hw; i < nc; i += 2 * NWARPS) {  // one half-warp per neighborhood, 4 features per lane
-          const int lo = sNbhLo[i], canon = sNbhLo[i + 1] - 1;
-          float4 ps = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-          for (int r = lo; r < canon; ++r) add4(ps, *reinterpret_cast<const float4*>(sStage + r * LDS_ + 4 * hl));
-          const size_t gofs = (size_t)(nb0 + i) * p.emb_ld + (size_t)l * F + 4 * hl;
-          *reinterpret_cast<float4*>(p.pool + gofs) = ps;                      // global_add_pool, count rows (gnn_model.py:107)
-          const float4 ha = *reinterpret_cast<const float4*>(sCh + i * F + 4 * hl);
-          *reinterpret_cast<float4*>(p.emb_a + gofs) = ha;                     // skip-concat of the canonical row (:275)
-          if (l < p.layers) {
-            float4 vt = make_float4(0.f, 0.f, 0.f, 0.f), vd = vt;
-            const int quirk = sQuirk[i];
-            for (int e = sEptr[canon], ee = sEptr[canon + 1]; e < ee; ++e) {
-              const int b = edge_at(e);
-              const int j = b & 127;
-              if (j == quirk) continue;
-              const float4 v = *reinterpret_cast<const float4*>(sStage + j * LDS_ + 4 * hl);
-              if (b & 0x80) add4(vt, v); else add4(vd, v);
-            }
-            *reinterpret_cast<float4*>(sCin + i * NB + 4 * hl) = vt;
-            *reinterpret_cast<float4*>(sCin + i * NB + F + 4 * hl) = vd;
-            *reinterpret_cast<float4*>(sCin + i * NB + 2 * F + 4 * hl) = ha;
-          }
-        }
-        if (l == p.layers) break;
-        tc05::fence_proxy_async_smem();  // A images written through the generic proxy -> visible to tcgen05.mma
-        __syncthreads();
-        lap(PH_POOL);
-
-        // ------------ tensor pipe: P = h . [W_tri | W_tride | W_self]  (one thread issues) ------------
-        if (tid == 0) {
+        // ------------ tensor pipe: P = h . [W_tri | W_tride | W_self], issued first so that it runs under the pool
+        // and canonical phases (one thread of the last warp issues: that warp is the least loaded in the pool phase)
+        if (l < p.layers && tid == ISSUER) {
           if (!tc05::mbar_wait(&bars[0], wphase)) timed_out = true;
           copy_pending = false;
           tc05::fence_after_sync();
@@ -368,33 +327,100 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
           }
           tc05::mma_commit(&bars[1]);
         }
-        wphase ^= 1;
-        lap(PH_ISSUE);
+        if (l < p.layers) wphase ^= 1;
+        // this thread's slice of the canonical-row weights of layer l: issued now, consumed after the pool phase
+        const uint8_t* wl = p.w_layers + (size_t)(l < p.layers ? l : 0) * LAYER_BYTES;
+        const int kq = tid & 7, kh = tid & 3;
+        float4 wa[NB / 32], wc[F / 16];
+        float bias_an = 0.f;
+        if (l < p.layers) {
+          const float* WaT = reinterpret_cast<const float*>(wl + OFF_WAT) + (size_t)(tid >> 3) * NB + 4 * kq;
+          const float* CwT = reinterpret_cast<const float*>(wl + OFF_CWT) + (size_t)(tid >> 2) * F + 4 * kh;
+#pragma unroll
+          for (int kk = 0; kk < NB / 32; ++kk) wa[kk] = __ldg(reinterpret_cast<const float4*>(WaT + 32 * kk));
+#pragma unroll
+          for (int kk = 0; kk < F / 16; ++kk) wc[kk] = __ldg(reinterpret_cast<const float4*>(CwT + 16 * kk));
+          bias_an = __ldg(reinterpret_cast<const float*>(wl + OFF_BIASA) + (tid >> 3));
+        }
+        // ------------ pool + canonical inputs of layer l (from the fp32 rows of h^l in sStage, h_a^l in sCh) ------------
+        // thread = (neighborhood, feature): 64 consecutive features per neighborhood, 8 neighborhoods at a time
+        {
+          const int f = tid & (F - 1);
+          for (int i = tid >> 6; i < nc; i += THREADS / F) {
+            const int lo = sNbhLo[i], canon = sNbhLo[i + 1] - 1;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int r = lo;
+            for (; r + 3 < canon; r += 4) {
+              s0 += sStage[r * LDS_ + f];
+              s1 += sStage[(r + 1) * LDS_ + f];
+              s2 += sStage[(r + 2) * LDS_ + f];
+              s3 += sStage[(r + 3) * LDS_ + f];
+            }
+            for (; r < canon; ++r) s0 += sStage[r * LDS_ + f];
+            const size_t gofs = (size_t)(nb0 + i) * p.emb_ld + (size_t)l * F + f;
+            p.pool[gofs] = (s0 + s1) + (s2 + s3);          // global_add_pool, count rows (gnn_model.py:107)
+            const float ha = sCh[i * F + f];
+            p.emb_a[gofs] = ha;                            // skip-concat of the canonical row (:275)
+            if (l < p.layers) {
+              float vt = 0.f, vd = 0.f;
+              const int quirk = sQuirk[i];
+              for (int e = sEptr[canon], ee = sEptr[canon + 1]; e < ee; ++e) {
+                const int b = edge_at(e);
+                const int j = b & 127;
+                const float v = (j == quirk) ? 0.f : sStage[j * LDS_ + f];
+                if (b & 0x80) vt += v; else vd += v;
+              }
+              sCin[i * NB + f] = vt;
+              sCin[i * NB + F + f] = vd;
+              sCin[i * NB + 2 * F + f] = ha;
+            }
+          }
+        }
+        if (l == p.layers) break;
+        __syncthreads();
+        lap(PH_POOL);
 
-        // ------------ CUDA cores meanwhile: canonical rows in fp32 (weights already in registers) ------------
+        // ------------ canonical rows in fp32 on the CUDA cores (weights in registers), two neighborhoods per trip ------------
         {
           const int n = tid >> 3;   // z_a = [sum_tri | sum_tride | h_a] . Wa : thread = (n, kq), k = 32 kk + 4 kq + {0..3}
           const int n2 = tid >> 2;  // cvec = h_a . [Cw_tri | Cw_tride]       : thread = (n2, kh), k = 16 kk + 4 kh + {0..3}
-          for (int r = 0; r < nc; ++r) {
-            const float* x = sCin + r * NB;
-            float va = 0.f, vc = 0.f;
+          for (int r = 0; r < nc; r += 2) {
+            const bool two = r + 1 < nc;
+            const float* x0 = sCin + r * NB;
+            const float* x1 = sCin + (two ? r + 1 : r) * NB;
+            float va0 = 0.f, va1 = 0.f, vc0 = 0.f, vc1 = 0.f;
 #pragma unroll
             for (int kk = 0; kk < NB / 32; ++kk) {
-              const float4 xv = *reinterpret_cast<const float4*>(x + 32 * kk + 4 * kq);
-              va = fmaf(xv.x, wa[kk].x, fmaf(xv.y, wa[kk].y, fmaf(xv.z, wa[kk].z, fmaf(xv.w, wa[kk].w, va))));
+              const float4 a0 = *reinterpret_cast<const float4*>(x0 + 32 * kk + 4 * kq);
+              const float4 a1 = *reinterpret_cast<const float4*>(x1 + 32 * kk + 4 * kq);
+              va0 = fmaf(a0.x, wa[kk].x, fmaf(a0.y, wa[kk].y, fmaf(a0.z, wa[kk].z, fmaf(a0.w, wa[kk].w, va0))));
+              va1 = fmaf(a1.x, wa[kk].x, fmaf(a1.y, wa[kk].y, fmaf(a1.z, wa[kk].z, fmaf(a1.w, wa[kk].w, va1))));
             }
 #pragma unroll
             for (int kk = 0; kk < F / 16; ++kk) {
-              const float4 xv = *reinterpret_cast<const float4*>(x + 2 * F + 16 * kk + 4 * kh);
-              vc = fmaf(xv.x, wc[kk].x, fmaf(xv.y, wc[kk].y, fmaf(xv.z, wc[kk].z, fmaf(xv.w, wc[kk].w, vc))));
+              const float4 a0 = *reinterpret_cast<const float4*>(x0 + 2 * F + 16 * kk + 4 * kh);
+              const float4 a1 = *reinterpret_cast<const float4*>(x1 + 2 * F + 16 * kk + 4 * kh);
+              vc0 = fmaf(a0.x, wc[kk].x, fmaf(a0.y, wc[kk].y, fmaf(a0.z, wc[kk].z, fmaf(a0.w, wc[kk].w, vc0))));
+              vc1 = fmaf(a1.x, wc[kk].x, fmaf(a1.y, wc[kk].y, fmaf(a1.z, wc[kk].z, fmaf(a1.w, wc[kk].w, vc1))));
             }
-            va += __shfl_xor_sync(FULL_MASK, va, 1);
-            vc += __shfl_xor_sync(FULL_MASK, vc, 1);
-            va += __shfl_xor_sync(FULL_MASK, va, 2);
-            vc += __shfl_xor_sync(FULL_MASK, vc, 2);
-            va += __shfl_xor_sync(FULL_MASK, va, 4);
-            if (kq == 0) sCh[r * F + n] = fmaxf(va + bias_an, 0.f);  // h_a^{l+1}; read again only after the next barrier
-            if (kh == 0) sCvec[r * 2 * F + n2] = vc;
+            va0 += __shfl_xor_sync(FULL_MASK, va0, 1);
+            va1 += __shfl_xor_sync(FULL_MASK, va1, 1);
+            vc0 += __shfl_xor_sync(FULL_MASK, vc0, 1);
+            vc1 += __shfl_xor_sync(FULL_MASK, vc1, 1);
+            va0 += __shfl_xor_sync(FULL_MASK, va0, 2);
+            va1 += __shfl_xor_sync(FULL_MASK, va1, 2);
+            vc0 += __shfl_xor_sync(FULL_MASK, vc0, 2);
+            vc1 += __shfl_xor_sync(FULL_MASK, vc1, 2);
+            va0 += __shfl_xor_sync(FULL_MASK, va0, 4);
+            va1 += __shfl_xor_sync(FULL_MASK, va1, 4);
+            if (kq == 0) {  // h_a^{l+1}; read again only after the next barriers
+              sCh[r * F + n] = fmaxf(va0 + bias_an, 0.f);
+              if (two) sCh[(r + 1) * F + n] = fmaxf(va1 + bias_an, 0.f);
+            }
+            if (kh == 0) {
+              sCvec[r * 2 * F + n2] = vc0;
+              if (two) sCvec[(r + 1) * 2 * F + n2] = vc1;
+            }
           }
         }
 
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         lap(PH_WAIT_MMA);
         mphase ^= 1;
         tc05::fence_after_sync();
-        if (tid == 0) {  // the B images are free again: stream in the next layer's (or the next tile's layer-0) weights
+        if (tid == ISSUER) {  // the B images are free again: stream in the next layer's (or the next tile's layer-0) weights
           const bool last = (tiles_done + 1 == my_tiles) && (l + 1 == p.layers);
           if (!last) {
             const int nl = (l + 1) % p.layers;
@@ -433,20 +459,37 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         lap(PH_T2S);
 
         // ------------ segmented, edge-type-split gather out of shared memory; one half-warp per row ------------
+        // the edge records of a row are fetched by the lanes of its half-warp in one go and broadcast by shuffle, so
+        // the P-row loads of consecutive edges are independent and overlap
         {
           const float4 bias = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(wl + OFF_BIASC) + 4 * hl);
-          for (int r = warp * 2 + hw; r < R; r += 2 * NWARPS) {
-            const int code = sRowCode[r];
-            if (code == 3) continue;  // canonical rows were done on the CUDA cores above
-            float4 acc = *reinterpret_cast<const float4*>(sStage + r * LDS_ + 4 * hl);  // P_self
-            add4(acc, bias);
-            const int eb = sEptr[r], ee = sEptr[r + 1];
-            for (int e = eb; e < ee; ++e) {
-              const int b = edge_at(e);
+          for (int rb = warp * 2; rb < R; rb += 2 * NWARPS) {
+            const int r = rb + hw;
+            const int code = (r < R) ? sRowCode[r] : 3;
+            const bool active = code != 3;  // canonical rows were done on the CUDA cores above
+            int eb = 0, ee = 0;
+            if (active) { eb = sEptr[r]; ee = sEptr[r + 1]; }
+            const int deg = ee - eb;
+            const int nsh = min(deg, 16);
+            const int myb = (hl < nsh) ? edge_at(eb + hl) : 0;
+            const int nmax = max(nsh, __shfl_xor_sync(FULL_MASK, nsh, 16));
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) {
+              acc = *reinterpret_cast<const float4*>(sStage + r * LDS_ + 4 * hl);  // P_self
+              add4(acc, bias);
+            }
+#pragma unroll 4
+            for (int k = 0; k < nmax; ++k) {
+              const int b = __shfl_sync(FULL_MASK, myb, k, 16);
               // (an edge to the canonical row adds its P row, which is exactly 0: canonical rows of A are zero and
               //  the canonical -> count message arrives through cvec instead)
+              if (k < nsh) add4(acc, *reinterpret_cast<const float4*>(sP + (b & 127) * LDP + ((b & 0x80) ? 0 : F) + 4 * hl));
+            }
+            for (int e = eb + 16; e < ee; ++e) {
+              const int b = edge_at(e);
               add4(acc, *reinterpret_cast<const float4*>(sP + (b & 127) * LDP + ((b & 0x80) ? 0 : F) + 4 * hl));
             }
+            if (!active) continue;
             if (code) add4(acc, *reinterpret_cast<const float4*>(sCvec + sRowG[r] * 2 * F + (code - 1) * F + 4 * hl));
             acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
             *reinterpret_cast<float4*>(sStage + r * LDS_ + 4 * hl) = acc;  // h^{l+1}, fp32 (pooling, canonical inputs)
@@ -458,6 +501,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
             *reinterpret_cast<uint2*>(sAlo + off) = *reinterpret_cast<const uint2*>(lo);
           }
         }
+        tc05::fence_proxy_async_smem();  // A images written through the generic proxy -> visible to tcgen05.mma
         __syncthreads();
         lap(PH_GATHER);
       }
@@ -465,7 +509,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
       ++tiles_done;
     }
   }
-  if (tid == 0 && copy_pending) tc05::mbar_wait(&bars[0], wphase);  // never exit with a bulk copy in flight
+  if (tid == ISSUER && copy_pending) tc05::mbar_wait(&bars[0], wphase);  // never exit with a bulk copy in flight
   if (timed_out) atomicExch(p.status, DESCO_ECUDA);
   tc05::fence_before_sync();
   __syncthreads();

@@ -25,3 +25,13 @@ int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge
 int desco_internal_dense_tc(const float* X, int ldx, const void* Wimg, const float* bias, const float* R, int ldr, float* Y,
                             int ldy, int M, int K, int N, int nblk, int act, float slope, int passes, int32_t* status,
                             cudaStream_t s);
+
+// post_mp chain Z[G, K0] -> out[G, 64] in one launch, fp32 (csrc/readout.cu).  Weights row-major [in][out].
+int desco_internal_readout_chain(const float* Z, int ldz, int K0, int G, const float* P0, const float* b0, const float* P1,
+                                 const float* b1, const float* P2, const float* b2, const float* P3, const float* b3,
+                                 float* out, cudaStream_t s);
+
+// Factorised count head for Q <= 32 queries in one launch, fp32 (csrc/readout.cu); DESCO_ERANGE for larger Q.
+int desco_internal_count_head_fused(const float* emb_t, int G, const float* emb_q, int Q, const float* W1a, const float* W1b,
+                                    const float* b1, const float* w2, const float* b2, float* pred, float* count,
+                                    cudaStream_t s);

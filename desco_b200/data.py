@@ -77,6 +77,42 @@ class DeviceCSR:
         return DeviceCSR(up(csr.rowptr), up(csr.col), up(csr.graph_ptr), max(mg, 1), csr)
 
 
+def gen_powerlaw_device(n: int, m_undirected: int, seed: int = 0, gamma: float = 2.5, max_deg_frac: float = 0.002,
+                        device=None) -> DeviceCSR:
+    """Config 5 built directly in HBM (same Chung-Lu recipe as ``graph.gen_powerlaw``, torch RNG on the device, so a
+    10M-node / 100M-edge target takes seconds instead of minutes of host numpy).  Benchmark input generation only."""
+    dev = _require_cuda(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + 505)
+    w = torch.arange(1, n + 1, dtype=torch.float64, device=dev) ** (-1.0 / (gamma - 1.0))
+    w = w * (2.0 * m_undirected / w.sum())
+    w = torch.clamp(w, max=max(max_deg_frac * n, 8.0))
+    cdf = torch.cumsum(w / w.sum(), 0)
+    k = int(m_undirected)
+    a = torch.searchsorted(cdf, torch.rand(k, dtype=torch.float64, device=dev, generator=g)).clamp_(0, n - 1)
+    b = torch.searchsorted(cdf, torch.rand(k, dtype=torch.float64, device=dev, generator=g)).clamp_(0, n - 1)
+    del cdf, w
+    child = torch.arange(1, n, dtype=torch.int64, device=dev)
+    parent = (torch.rand(n - 1, dtype=torch.float64, device=dev, generator=g) * child).to(torch.int64)
+    perm = torch.randperm(n, device=dev, generator=g)
+    u = perm[torch.cat([a, child])]
+    v = perm[torch.cat([b, parent])]
+    del a, b, child, parent, perm
+    keep = u != v
+    u, v = u[keep], v[keep]
+    key = torch.unique(torch.cat([u * n + v, v * n + u]))  # sorted: row-major, ascending columns, deduplicated
+    del u, v, keep
+    src = key // n
+    col = (key - src * n).to(torch.int32)
+    del key
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    rowptr[1:] = torch.cumsum(torch.bincount(src, minlength=n), 0)
+    if int(rowptr[-1]) >= 2**31:
+        raise ValueError("target graph exceeds int32 edge offsets")
+    graph_ptr = torch.tensor([0, n], dtype=torch.int32, device=dev)
+    return DeviceCSR(rowptr.to(torch.int32), col, graph_ptr, n, None)
+
+
 @dataclass
 class NeighborhoodBatch:
     """Packed canonical neighborhoods in HBM.  Row order inside a neighborhood = ascending node id, so the canonical
