@@ -89,6 +89,10 @@ SIGNATURES = {
     "desco_partition_scan_workspace_bytes": (_L, [_I]),
     "desco_partition_scan": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
     "desco_partition_fill": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "desco_partition_large_workspace_bytes": (_L, [_I, _I]),
+    "desco_partition_large_count": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
+    "desco_partition_large_fill": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
+    "desco_partition_large_set_caps": (_I, [_I, _I, _I, _I, _I, _I]),
     "desco_shmp_edge_types": (_I, [_VP, _VP, _I, _VP, _VP]),
     "desco_shmp_workspace_bytes": (_L, [_I, _I, _I]),
     "desco_shmp_layer_weight_floats": (_L, []),
@@ -103,6 +107,17 @@ SIGNATURES = {
     "desco_gossip_layer0": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP]),
     "desco_gossip_layer1": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP]),
     "desco_shmp_fused_phase_cycles": (_I, [_VP, _I]),
+    "desco_train_plan": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP]),
+    "desco_train_aggregate": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP, _I, _VP, _I, _VP, _I, _VP, _I, _VP]),
+    "desco_train_dense": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _I, _VP, _I, _I, _I, _I, _F, _I, _VP]),
+    "desco_train_wgrad": (_I, [_VP, _I, _I, _VP, _I, _I, _I, _VP, _VP, _VP, _I, _VP]),
+    "desco_train_act_backward": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _F, _VP]),
+    "desco_train_fill_rows": (_I, [_VP, _I, _I, _I, _VP, _VP]),
+    "desco_train_colsum": (_I, [_VP, _I, _I, _I, _VP, _VP]),
+    "desco_train_pool": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _I, _VP, _I, _VP, _I, _VP]),
+    "desco_train_head_loss": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP]),
+    "desco_train_head_backward": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "desco_train_adam": (_I, [_VP, _VP, _VP, _VP, _L, _F, _F, _F, _F, _F, _I, _VP]),
     "desco_tc_selftest": (_I, [_VP, _VP, _I, _I, _VP, _VP, _VP]),
     "desco_gossip_forward": (_I, [_VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _L, _I, _VP]),
 }

@@ -201,16 +201,19 @@ __global__ void __launch_bounds__(256) partition_kernel(
     // fill pass inputs / outputs (fill == 1)
     int fill, const int32_t* __restrict__ node_off, const int32_t* __restrict__ edge_off,
     int32_t* __restrict__ node_gid, int32_t* __restrict__ edge_ptr, int32_t* __restrict__ edge_col,
-    uint8_t* __restrict__ edge_tri, int32_t* __restrict__ status) {
+    uint8_t* __restrict__ edge_tri, int32_t* __restrict__ status,
+    // dense tier of the large-graph path: bitsets in a per-CTA slice of global scratch, only centres of class `klass_want`
+    uint32_t* __restrict__ gscratch = nullptr, const uint8_t* __restrict__ klass = nullptr, int klass_want = 0) {
   extern __shared__ uint32_t smem[];
   const int groups_per_cta = CTA ? 1 : (blockDim.x >> 5);
   const int g_in_cta = CTA ? 0 : warp_id();
-  uint32_t* S = smem + (size_t)g_in_cta * 4 * max_words;
+  uint32_t* S = gscratch ? gscratch + (size_t)blockIdx.x * 4 * max_words : smem + (size_t)g_in_cta * 4 * max_words;
   uint32_t* F = S + max_words;
   uint32_t* Nx = F + max_words;
   uint32_t* aux = Nx + max_words;
 
   for (int ci = blockIdx.x * groups_per_cta + g_in_cta; ci < num_centres; ci += gridDim.x * groups_per_cta) {
+    if (klass && klass[ci] != klass_want) continue;
     const int centre = centres[ci];
     int gid;
     if (fill) {
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(256) partition_kernel(
           if (v > limit) break;
           if (!bit_test(S, v - lo)) continue;
           edge_col[out] = n0 + local_index(S, pref, v - lo);
-          edge_tri[out] = has_common_neighbour(rowptr, col, S, lo, limit, u, v) ? 1 : 0;
+          edge_tri[out] = (gscratch == nullptr && has_common_neighbour(rowptr, col, S, lo, limit, u, v)) ? 1 : 0;
           ++out;
         }
         ++k;
@@ -572,6 +575,35 @@ int launch_partition_small(const int32_t* rowptr, const int32_t* col, const int3
   return DESCO_OK;
 }
 
+// do two ascending index lists share an element?  Similar lengths: linear merge; a short list against a long one
+// (a leaf against a hub row - power-law targets): gallop through the long list by binary search, O(short * log long).
+__device__ __forceinline__ bool sorted_lists_intersect(const int32_t* __restrict__ idx, int a, int ae, int b, int be) {
+  if (ae - a > be - b) {
+    int t = a; a = b; b = t;
+    t = ae; ae = be; be = t;
+  }
+  if (ae == a) return false;
+  if (be - b < 8 * (ae - a)) {
+    while (a < ae && b < be) {
+      const int x = idx[a], y = idx[b];
+      if (x == y) return true;
+      if (x < y) ++a; else ++b;
+    }
+    return false;
+  }
+  for (; a < ae && b < be; ++a) {
+    const int x = idx[a];
+    int lo = b, hi = be;  // first position with idx[pos] >= x
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (idx[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    if (lo < be && idx[lo] == x) return true;
+    b = lo;
+  }
+  return false;
+}
+
 // ToTconvHetero on an existing packed batch: one warp per row, one lane per incident edge.
 __global__ void edge_types_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ edge_col,
                                   int num_rows, uint8_t* __restrict__ edge_tri) {
@@ -579,16 +611,388 @@ __global__ void edge_types_kernel(const int32_t* __restrict__ edge_ptr, const in
   if (row >= num_rows) return;
   const int rb = edge_ptr[row], re = edge_ptr[row + 1];
   for (int e = rb + lane_id(); e < re; e += 32) {
-    int v = edge_col[e];
-    int a = rb, b = edge_ptr[v], be = edge_ptr[v + 1];
-    bool tri = false;
-    while (a < re && b < be) {
-      int x = edge_col[a], y = edge_col[b];
-      if (x == y) { tri = true; break; }
-      if (x < y) ++a; else ++b;
-    }
-    edge_tri[e] = tri ? 1 : 0;
+    const int v = edge_col[e];
+    edge_tri[e] = sorted_lists_intersect(edge_col, rb, re, edge_ptr[v], edge_ptr[v + 1]) ? 1 : 0;
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Large-graph regime (config 5: one 10M-node / 200M-directed-edge power-law target).  A bitset over the target no
+// longer fits shared memory and would cost O(N/32) per centre, so the set state of a centre is SPARSE:
+//   * an open-addressing hash set of node ids (linear probing, atomicCAS insert; bit 31 of a key = "reached" flag),
+//   * the member list L in discovery order (BFS levels are contiguous slices of it),
+//   * the reached list R (component of the centre), bitonic-sorted at the end so that rows come out in ascending node
+//     id and a local id is a binary search.
+// Tier 0 keeps all three in shared memory; a centre whose ball overflows them is re-run by tier 1 (same code, tables in
+// a per-CTA slice of global scratch, L2-resident), and a ball that overflows that too by the dense tier (the bitset
+// kernel above with its four bitsets in global scratch).  The sorted adjacency makes "<= centre" a PREFIX of every
+// row, so the restricted passes stop at the first neighbour above the centre.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t SP_EMPTY = 0xffffffffu;
+constexpr uint32_t SP_FLAG = 0x80000000u;
+constexpr uint32_t SP_MASK = 0x7fffffffu;
+constexpr int SP_THREADS = 256;
+
+struct SparseArgs {
+  const int32_t* rowptr; const int32_t* col; const int32_t* graph_ptr; int num_graphs;
+  const int32_t* centres; int num_centres, depth, mode;
+  int32_t* out_nv; int32_t* out_ne; int32_t* centre_graph;
+  int fill; const int32_t* node_off; const int32_t* edge_off;
+  int32_t* node_gid; int32_t* edge_ptr; int32_t* edge_col;
+  uint8_t* klass; int tier;      // centre class: 0 = tier 0 (shared memory), 1 = tier 1 (global scratch), 2 = dense tier
+  uint32_t* gscratch;            // tier 1: per-CTA slice of (H + capL + capR) words
+  int log2H, capL, capR;         // hash slots (power of two), member-list / reached-list capacities (capR power of two)
+};
+
+struct SparseSet {
+  uint32_t* keys; uint32_t* L; uint32_t* R;
+  int H, log2H, capL, capR;
+  int* nL; int* nR; int* over;   // shared counters
+
+  __device__ __forceinline__ uint32_t slot_of(int v) const { return ((uint32_t)v * 2654435761u) >> (32 - log2H); }
+  // returns true if v was not a member yet (and appends it to L)
+  __device__ __forceinline__ bool insert(int v) {
+    uint32_t h = slot_of(v);
+    while (true) {
+      const uint32_t old = atomicCAS(&keys[h], SP_EMPTY, (uint32_t)v);
+      if (old == SP_EMPTY) {
+        const int idx = atomicAdd(nL, 1);
+        if (idx < capL) L[idx] = (uint32_t)v; else *over = 1;
+        return true;
+      }
+      if ((old & SP_MASK) == (uint32_t)v) return false;
+      if (*reinterpret_cast<volatile int*>(over)) return false;
+      h = (h + 1) & (H - 1);
+    }
+  }
+  __device__ __forceinline__ int find(int v) const {  // slot or -1
+    uint32_t h = slot_of(v);
+    while (true) {
+      const uint32_t k = keys[h];
+      if (k == SP_EMPTY) return -1;
+      if ((k & SP_MASK) == (uint32_t)v) return (int)h;
+      h = (h + 1) & (H - 1);
+    }
+  }
+  __device__ __forceinline__ bool reached(int v) const {
+    const int s = find(v);
+    return s >= 0 && (keys[s] & SP_FLAG);
+  }
+  __device__ __forceinline__ int local_id(int v, int n) const {  // index of v in the sorted R[0,n)
+    int a = 0, b = n;
+    while (a < b) {
+      const int m = (a + b) >> 1;
+      if ((int)R[m] < v) a = m + 1; else b = m;
+    }
+    return a;
+  }
+};
+
+template <bool GLOBAL>
+__global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const SparseArgs p) {
+  extern __shared__ uint32_t sp_smem[];
+  __shared__ int s_nL, s_nR, s_over, s_cnt, s_gid;
+  SparseSet set;
+  set.log2H = p.log2H; set.H = 1 << p.log2H; set.capL = p.capL; set.capR = p.capR;
+  set.keys = GLOBAL ? p.gscratch + (size_t)blockIdx.x * ((size_t)set.H + p.capL + p.capR) : sp_smem;
+  set.L = set.keys + set.H;
+  set.R = set.L + p.capL;
+  set.nL = &s_nL; set.nR = &s_nR; set.over = &s_over;
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  constexpr int NW = SP_THREADS / 32;
+  const int32_t* __restrict__ rowptr = p.rowptr;
+  const int32_t* __restrict__ col = p.col;
+
+  bool table_ready = false;  // tier 1 wipes its 2 MB table only if it really owns a centre
+
+  for (int ci = blockIdx.x; ci < p.num_centres; ci += gridDim.x) {
+    if (p.fill) {
+      if (p.klass[ci] != p.tier || p.out_ne[ci] == 0) continue;
+    } else if (p.tier != 0 && p.klass[ci] != p.tier) {
+      continue;
+    }
+    if (!table_ready) {
+      for (int i = tid; i < set.H; i += SP_THREADS) set.keys[i] = SP_EMPTY;
+      table_ready = true;
+      __syncthreads();
+    }
+    const int centre = p.centres[ci];
+    const int limit = (p.mode == DESCO_MODE_KHOP) ? 0x7fffffff : centre;
+    if (tid == 0) {
+      s_nL = 0; s_nR = 0; s_over = 0; s_cnt = 0;
+      int a = 0, b = p.num_graphs;  // largest a with graph_ptr[a] <= centre
+      while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (p.graph_ptr[mid] <= centre) a = mid; else b = mid;
+      }
+      s_gid = a;
+    }
+    __syncthreads();
+    if (tid == 0) set.insert(centre);
+    __syncthreads();
+
+    // ---- phase A: k levels of frontier expansion (data.py:329-350); one warp per frontier node ----
+    int lb = 0, le = 1;
+    bool over = false;
+    for (int level = 0; level < p.depth && lb < le && !over; ++level) {
+      const bool restricted = p.mode == DESCO_MODE_CANONICAL || (p.mode == DESCO_MODE_HETERO && level == p.depth - 1);
+      for (int i = lb + warp; i < le; i += NW) {
+        const int u = (int)set.L[i];
+        const int rb = rowptr[u], re = rowptr[u + 1];
+        for (int e0 = rb; e0 < re; e0 += 32) {
+          const int e = e0 + lane;
+          const int v = (e < re) ? col[e] : 0x7fffffff;
+          const bool above = restricted && e < re && v > centre;
+          if (e < re && !above) set.insert(v);
+          if (__any_sync(FULL_MASK, above)) break;  // sorted row: nothing further passes
+        }
+      }
+      __syncthreads();
+      lb = le;
+      le = min(s_nL, p.capL);
+      over = s_over != 0;
+      __syncthreads();
+    }
+
+    // ---- phase B + C: candidates <= centre (data.py:385), component of the centre inside them (:387-390) ----
+    if (!over) {
+      if (p.mode == DESCO_MODE_HETERO) {
+        if (tid == 0) {
+          const int s = set.find(centre);
+          set.keys[s] |= SP_FLAG;
+          set.R[0] = (uint32_t)centre;
+          s_nR = 1;
+        }
+        __syncthreads();
+        int qb = 0, qe = 1;
+        while (qb < qe && !over) {
+          for (int i = qb + warp; i < qe; i += NW) {
+            const int u = (int)set.R[i];
+            const int rb = rowptr[u], re = rowptr[u + 1];
+            for (int e0 = rb; e0 < re; e0 += 32) {
+              const int e = e0 + lane;
+              const int v = (e < re) ? col[e] : 0x7fffffff;
+              if (e < re && v <= centre) {
+                const int s = set.find(v);
+                if (s >= 0 && !(set.keys[s] & SP_FLAG)) {
+                  const uint32_t old = atomicOr(&set.keys[s], SP_FLAG);
+                  if (!(old & SP_FLAG)) {
+                    const int idx = atomicAdd(&s_nR, 1);
+                    if (idx < set.capR) set.R[idx] = (uint32_t)v; else s_over = 1;
+                  }
+                }
+              }
+              if (__any_sync(FULL_MASK, e < re && v > centre)) break;
+            }
+          }
+          __syncthreads();
+          qb = qe;
+          qe = min(s_nR, set.capR);
+          over = s_over != 0;
+          __syncthreads();
+        }
+      } else {  // restricted BFS / plain k-hop ball: every member is in the result
+        const int n = s_nL;
+        if (n > set.capR) {
+          if (tid == 0) s_over = 1;
+        } else {
+          for (int i = tid; i < n; i += SP_THREADS) {
+            const int v = (int)set.L[i];
+            set.R[i] = (uint32_t)v;
+            set.keys[set.find(v)] |= SP_FLAG;
+          }
+          if (tid == 0) s_nR = n;
+        }
+        __syncthreads();
+        over = s_over != 0;
+      }
+    }
+
+    if (over) {
+      // this tier cannot hold the ball: hand the centre to the next tier and wipe the table
+      if (tid == 0 && !p.fill) {
+        p.klass[ci] = (uint8_t)(p.tier + 1);
+        p.out_nv[ci] = 0;
+        p.out_ne[ci] = 0;
+        p.centre_graph[ci] = s_gid;
+      }
+      __syncthreads();
+      for (int i = tid; i < set.H; i += SP_THREADS) set.keys[i] = SP_EMPTY;
+      __syncthreads();
+      continue;
+    }
+
+    // ---- phase D: sort the reached list -> ascending node ids (canonical node = last row) ----
+    const int nv = s_nR;
+    int n2 = 1;
+    while (n2 < nv) n2 <<= 1;
+    for (int i = nv + tid; i < n2; i += SP_THREADS) set.R[i] = 0x7fffffffu;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < n2; i += SP_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const uint32_t a = set.R[i], b = set.R[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) {
+              set.R[i] = b;
+              set.R[ixj] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- induced degrees (count pass: just the total) ----
+    const int n0 = p.fill ? p.node_off[ci] : 0;
+    const int eo = p.fill ? p.edge_off[ci] : 0;
+    for (int i = warp; i < nv; i += NW) {
+      const int u = (int)set.R[i];
+      const int rb = rowptr[u], re = rowptr[u + 1];
+      int cnt = 0;
+      for (int e0 = rb; e0 < re; e0 += 32) {
+        const int e = e0 + lane;
+        const int v = (e < re) ? col[e] : 0x7fffffff;
+        if (e < re && v <= limit && set.reached(v)) ++cnt;
+        if (__any_sync(FULL_MASK, e < re && v > limit)) break;
+      }
+      cnt = warp_sum(cnt);
+      if (lane == 0) {
+        if (p.fill) {
+          p.node_gid[n0 + i] = u;
+          p.edge_ptr[n0 + 1 + i] = cnt;
+        } else {
+          atomicAdd(&s_cnt, cnt);
+        }
+      }
+    }
+    __syncthreads();
+    if (!p.fill) {
+      if (tid == 0) {
+        const int ne = s_cnt;
+        p.out_ne[ci] = ne;
+        p.out_nv[ci] = ne > 0 ? nv : 0;  // edge-free neighborhoods are dropped (workload.py:253-256)
+        p.centre_graph[ci] = s_gid;
+        if (p.tier == 0) p.klass[ci] = 0;
+      }
+    } else {
+      if (n0 == 0 && tid == 0) p.edge_ptr[0] = 0;
+      if (warp == 0) {  // in-place inclusive scan of the row degrees
+        int carry = eo;
+        for (int base = 0; base < nv; base += 32) {
+          const int x = (base + lane < nv) ? p.edge_ptr[n0 + 1 + base + lane] : 0;
+          const int incl = warp_incl_scan(x);
+          if (base + lane < nv) p.edge_ptr[n0 + 1 + base + lane] = carry + incl;
+          carry += __shfl_sync(FULL_MASK, incl, 31);
+        }
+      }
+      __syncthreads();
+      // edges in adjacency order (ascending node id == ascending local id); types follow in edge_types_kernel
+      for (int i = warp; i < nv; i += NW) {
+        const int u = (int)set.R[i];
+        const int rb = rowptr[u], re = rowptr[u + 1];
+        int out = (i == 0) ? eo : p.edge_ptr[n0 + i];
+        for (int e0 = rb; e0 < re; e0 += 32) {
+          const int e = e0 + lane;
+          const int v = (e < re) ? col[e] : 0x7fffffff;
+          const bool ok = e < re && v <= limit && set.reached(v);
+          const uint32_t m = __ballot_sync(FULL_MASK, ok);
+          if (ok) p.edge_col[out + __popc(m & ((1u << lane) - 1u))] = n0 + set.local_id(v, nv);
+          out += __popc(m);
+          if (__any_sync(FULL_MASK, e < re && v > limit)) break;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- wipe the table: tier 0 clears all slots, tier 1 only the members' ----
+    if (!GLOBAL || s_nL > set.H / 16) {
+      for (int i = tid; i < set.H; i += SP_THREADS) set.keys[i] = SP_EMPTY;
+    } else {
+      const int n = s_nL;
+      for (int i = tid; i < n; i += SP_THREADS) set.L[i] = (uint32_t)set.find((int)set.L[i]);
+      __syncthreads();
+      for (int i = tid; i < n; i += SP_THREADS) set.keys[set.L[i]] = SP_EMPTY;
+    }
+    __syncthreads();
+  }
+}
+
+// tunables of the large-graph path (desco_partition_large_set_caps lets the tests force every tier on small graphs)
+int g_sp_log2h0 = 13, g_sp_capl0 = 5120, g_sp_capr0 = 4096;      // tier 0: 32 + 20 + 16 KB of shared memory
+int g_sp_log2h1 = 19, g_sp_capl1 = 1 << 18, g_sp_capr1 = 1 << 18;  // tier 1: 4 MB of global scratch per CTA
+
+struct LargeLayout {
+  size_t klass_off, t1_off, t2_off, bytes;
+  int t1_ctas, t2_ctas, max_words;
+  size_t t1_words;
+};
+
+LargeLayout large_layout(int max_graph_nodes, int num_centres) {
+  LargeLayout l;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const int sms = desco_num_sms();
+  l.max_words = (max_graph_nodes + 31) / 32;
+  l.t1_ctas = 4 * sms;  // tier 1 is latency bound on L2 hash probes: four 256-thread CTAs per SM
+  l.t2_ctas = sms;
+  l.t1_words = ((size_t)1 << g_sp_log2h1) + g_sp_capl1 + g_sp_capr1;
+  l.klass_off = 0;
+  l.t1_off = up((size_t)(num_centres > 0 ? num_centres : 1));
+  l.t2_off = l.t1_off + up(l.t1_words * 4 * l.t1_ctas);
+  l.bytes = l.t2_off + up((size_t)4 * l.max_words * 4 * l.t2_ctas);
+  return l;
+}
+
+int launch_partition_large(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int num_graphs,
+                           const int32_t* centres, int num_centres, int depth, int mode, int max_graph_nodes,
+                           int32_t* nv, int32_t* ne, int32_t* centre_graph, int fill, const int32_t* node_off,
+                           const int32_t* edge_off, int32_t* node_gid, int32_t* edge_ptr, int32_t* edge_col,
+                           uint8_t* edge_tri, int32_t* status, void* workspace, int64_t workspace_bytes,
+                           cudaStream_t stream) {
+  if (depth < 0 || mode < DESCO_MODE_HETERO || mode > DESCO_MODE_KHOP || max_graph_nodes <= 0 || num_centres < 0)
+    return DESCO_EINVAL;
+  if (num_centres == 0) return DESCO_OK;
+  if (!rowptr || !col || !graph_ptr || !centres || !nv || !ne || !centre_graph || !status || !workspace) return DESCO_EINVAL;
+  const LargeLayout l = large_layout(max_graph_nodes, num_centres);
+  if ((int64_t)l.bytes > workspace_bytes) return DESCO_ENOMEM;
+  uint8_t* base = (uint8_t*)workspace;
+  const int sms = desco_num_sms();
+  SparseArgs a;
+  a.rowptr = rowptr; a.col = col; a.graph_ptr = graph_ptr; a.num_graphs = num_graphs;
+  a.centres = centres; a.num_centres = num_centres; a.depth = depth; a.mode = mode;
+  a.out_nv = nv; a.out_ne = ne; a.centre_graph = centre_graph;
+  a.fill = fill; a.node_off = node_off; a.edge_off = edge_off; a.node_gid = node_gid; a.edge_ptr = edge_ptr; a.edge_col = edge_col;
+  a.klass = base + l.klass_off;
+  DescoProfScope prof(DESCO_PROF_PARTITION, stream, 3);
+  {  // tier 0: shared memory
+    a.tier = 0; a.gscratch = nullptr; a.log2H = g_sp_log2h0; a.capL = g_sp_capl0; a.capR = g_sp_capr0;
+    const size_t smem = (((size_t)1 << a.log2H) + a.capL + a.capR) * 4;
+    if (smem > 200 * 1024) return DESCO_EINVAL;
+    DESCO_CUDA_TRY(cudaFuncSetAttribute(partition_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    const int blocks = num_centres < sms * per_sm ? num_centres : sms * per_sm;
+    partition_sparse_kernel<false><<<blocks, SP_THREADS, smem, stream>>>(a);
+    DESCO_LAUNCH_CHECK();
+  }
+  {  // tier 1: global scratch
+    a.tier = 1; a.gscratch = (uint32_t*)(base + l.t1_off); a.log2H = g_sp_log2h1; a.capL = g_sp_capl1; a.capR = g_sp_capr1;
+    const int blocks = num_centres < l.t1_ctas ? num_centres : l.t1_ctas;
+    partition_sparse_kernel<true><<<blocks, SP_THREADS, 0, stream>>>(a);
+    DESCO_LAUNCH_CHECK();
+  }
+  {  // dense tier: bitsets over the whole target graph in global scratch
+    const int blocks = num_centres < l.t2_ctas ? num_centres : l.t2_ctas;
+    partition_kernel<true><<<blocks, 256, 0, stream>>>(rowptr, col, graph_ptr, num_graphs, centres, num_centres, depth, mode,
+                                                      l.max_words, nv, ne, centre_graph, fill, node_off, edge_off, node_gid,
+                                                      edge_ptr, edge_col, edge_tri, status,
+                                                      (uint32_t*)(base + l.t2_off), a.klass, 2);
+    DESCO_LAUNCH_CHECK();
+  }
+  return DESCO_OK;
 }
 
 struct KeepFlag {
@@ -734,6 +1138,45 @@ int desco_shmp_edge_types(const int32_t* edge_ptr, const int32_t* edge_col, int3
                                                                                                        num_rows, edge_tri);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;
+}
+
+int64_t desco_partition_large_workspace_bytes(int32_t max_graph_nodes, int32_t num_centres) {
+  return (int64_t)large_layout(max_graph_nodes, num_centres).bytes;
+}
+
+int desco_partition_large_set_caps(int32_t log2_slots0, int32_t members0, int32_t reached0, int32_t log2_slots1,
+                                   int32_t members1, int32_t reached1) {
+  auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
+  if (log2_slots0 < 4 || log2_slots0 > 15 || log2_slots1 < 4 || log2_slots1 > 26 || !pow2(reached0) || !pow2(reached1) ||
+      members0 < 1 || members1 < 1 || members0 + SP_THREADS > (1 << log2_slots0) || members1 + SP_THREADS > (1 << log2_slots1))
+    return DESCO_EINVAL;
+  g_sp_log2h0 = log2_slots0; g_sp_capl0 = members0; g_sp_capr0 = reached0;
+  g_sp_log2h1 = log2_slots1; g_sp_capl1 = members1; g_sp_capr1 = reached1;
+  return DESCO_OK;
+}
+
+int desco_partition_large_count(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
+                                const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
+                                int32_t max_graph_nodes, int32_t* out_nv, int32_t* out_ne, int32_t* out_centre_graph,
+                                int32_t* status, void* workspace, int64_t workspace_bytes, void* stream) {
+  return launch_partition_large(rowptr, col, graph_ptr, num_graphs, centres, num_centres, depth, mode, max_graph_nodes,
+                                out_nv, out_ne, out_centre_graph, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                status, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int desco_partition_large_fill(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
+                               const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
+                               int32_t max_graph_nodes, const int32_t* nv, const int32_t* ne, const int32_t* centre_graph,
+                               const int32_t* node_off, const int32_t* edge_off, int32_t num_rows, int32_t* node_gid,
+                               int32_t* edge_ptr, int32_t* edge_col, uint8_t* edge_tri, int32_t* status, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+  if (!node_off || !edge_off || !node_gid || !edge_ptr || !edge_col || !edge_tri || num_rows < 0) return DESCO_EINVAL;
+  const int rc = launch_partition_large(rowptr, col, graph_ptr, num_graphs, centres, num_centres, depth, mode,
+                                        max_graph_nodes, const_cast<int32_t*>(nv), const_cast<int32_t*>(ne),
+                                        const_cast<int32_t*>(centre_graph), 1, node_off, edge_off, node_gid, edge_ptr,
+                                        edge_col, edge_tri, status, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (rc) return rc;
+  return desco_shmp_edge_types(edge_ptr, edge_col, num_rows, edge_tri, stream);  // SHMP types of the whole packed batch
 }
 
 const char* desco_version(void) { return "desco_b200 0.1 sm_100a"; }

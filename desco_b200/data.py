@@ -181,13 +181,19 @@ class NeighborhoodBatch:
         )
 
 
+LARGE_GRAPH_NODES = 409_600  # above this the four node bitsets of a centre no longer fit shared memory
+
+
 def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: int, mode: Union[int, str] = "hetero",
-                    ) -> NeighborhoodBatch:
+                    large: Optional[bool] = None) -> NeighborhoodBatch:
     """All canonical neighborhoods of ``centres`` (default: every node, in dataset order) in one packed batch.
 
-    Replaces the double Python loop of ``NeighborhoodDataset.process`` (``workload.py:250-272``)."""
+    Replaces the double Python loop of ``NeighborhoodDataset.process`` (``workload.py:250-272``).  ``large`` selects
+    the sparse (hash-set) kernels of the large-graph regime; default: by ``graph.max_graph_nodes``."""
     lib = _lib.load()
     dev = graph.rowptr.device
+    if large is None:
+        large = graph.max_graph_nodes > LARGE_GRAPH_NODES
     if isinstance(mode, str):
         mode = {"hetero": MODE_HETERO, "canonical": MODE_CANONICAL, "khop": MODE_KHOP}[mode]
     if centres is None:
@@ -204,31 +210,49 @@ def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: in
     totals, status = small[:3], small[3:]
     with torch.cuda.device(dev):
         st = _stream()
-        _lib.check(lib.desco_partition_count(
-            _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres), C, depth, mode,
-            graph.max_graph_nodes, _ptr(nv), _ptr(ne), _ptr(cg), _ptr(status), st), "desco_partition_count")
+        if large:
+            lbytes = int(lib.desco_partition_large_workspace_bytes(graph.max_graph_nodes, C))
+            lwork = torch.empty(lbytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.desco_partition_large_count(
+                _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres), C, depth,
+                mode, graph.max_graph_nodes, _ptr(nv), _ptr(ne), _ptr(cg), _ptr(status), _ptr(lwork), lbytes, st),
+                "desco_partition_large_count")
+        else:
+            _lib.check(lib.desco_partition_count(
+                _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres), C, depth,
+                mode, graph.max_graph_nodes, _ptr(nv), _ptr(ne), _ptr(cg), _ptr(status), st), "desco_partition_count")
         wbytes = int(lib.desco_partition_scan_workspace_bytes(C))
         work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
         _lib.check(lib.desco_partition_scan(
             _ptr(centres), _ptr(nv), _ptr(ne), C, _ptr(rank), _ptr(noff), _ptr(eoff), _ptr(nbh_ptr), _ptr(centre_out),
             _ptr(indicator), _ptr(totals), _ptr(work), wbytes, st), "desco_partition_scan")
-        G, V, E, code = (int(x) for x in small.cpu())  # the one host sync of the partition: output sizes
+        mx = nv[:C].max().reshape(1) if C else torch.zeros(1, **i32)
+        G, V, E, code, max_nv = (int(x) for x in torch.cat([small, mx]).cpu())  # the one host sync: output sizes
         if code != 0:
             _lib.check(code, "partition kernel (device status)")
         node_gid = torch.empty(V, **i32)
         edge_ptr = torch.zeros(V + 1, **i32)
         edge_col = torch.empty(E, **i32)
         edge_tri = torch.empty(E, dtype=torch.uint8, device=dev)
-        if V > 0:
+        if V > 0 and large:
+            _lib.check(lib.desco_partition_large_fill(
+                _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres), C, depth,
+                mode, graph.max_graph_nodes, _ptr(nv), _ptr(ne), _ptr(cg), _ptr(noff), _ptr(eoff), V, _ptr(node_gid),
+                _ptr(edge_ptr), _ptr(edge_col), _ptr(edge_tri), _ptr(status), _ptr(lwork), lbytes, st),
+                "desco_partition_large_fill")
+        elif V > 0:
             _lib.check(lib.desco_partition_fill(
                 _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres), C, depth,
                 mode, graph.max_graph_nodes, _ptr(nv), _ptr(ne), _ptr(cg), _ptr(noff), _ptr(eoff), _ptr(node_gid),
                 _ptr(edge_ptr), _ptr(edge_col), _ptr(edge_tri), _ptr(status), st), "desco_partition_fill")
-    return NeighborhoodBatch(
+    batch = NeighborhoodBatch(
         nbh_ptr[: G + 1], node_gid, edge_ptr, edge_col, edge_tri, centre_out[:G], indicator[:C], cg[:C],
         graph.graph_ptr, G, V, E, hetero=(mode == MODE_HETERO),
-        max_rows=graph.max_graph_nodes,  # a neighborhood never leaves its target graph
+        max_rows=max_nv,  # rows of the largest neighborhood (selects the fused SHMP kernel)
     )
+    if large:
+        batch._cache["tier"] = lwork[:C].clone()  # which tier served each centre (0 shared, 1 global hash, 2 dense)
+    return batch
 
 
 def shmp_edge_types(edge_ptr: torch.Tensor, edge_col: torch.Tensor) -> torch.Tensor:

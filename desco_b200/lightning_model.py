@@ -177,6 +177,31 @@ class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
     def forward(self, batch):
         return self.graph_to_count(batch)
 
+    # ---- training (csrc/train.cu through desco_b200/training.py) ----
+    def train_forward(self, batch, batch_idx=0) -> torch.Tensor:
+        """``lightning_model.py:228-254``: mean over the queries of ``smooth_l1(pred_q, log2(batch.y[:, q] + 1))``.
+        The returned scalar carries a grad_fn over the target GNN, the query GNN and the count head."""
+        from .training import train_forward
+
+        return train_forward(self, batch)
+
+    def training_step(self, batch, batch_idx=0) -> torch.Tensor:  # :133-136
+        return self.train_forward(batch, batch_idx)
+
+    def validation_step(self, batch, batch_idx=0) -> torch.Tensor:  # :147-154
+        return self.train_forward(batch, batch_idx).detach()
+
+    def criterion(self, count: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:  # :285-289
+        return torch.nn.functional.smooth_l1_loss(count, truth)
+
+    def configure_optimizers(self):
+        """``lightning_model.py:160-173``: Adam(lr, weight_decay) + ReduceLROnPlateau(min, 0.5, patience 20, 1e-5)."""
+        from .training import FusedAdam
+
+        opt = FusedAdam(self.parameters(), lr=getattr(self, "lr", 1e-4), weight_decay=getattr(self, "weight_decay", 0.0))
+        sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.5, patience=20, min_lr=1e-5)
+        return {"optimizer": opt, "lr_scheduler": sched, "monitor": "neighborhood_counting_val_loss"}
+
 
 def default_gossip_args(**kw) -> SimpleNamespace:
     """``config.py:312-322``."""

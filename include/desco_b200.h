@@ -87,6 +87,29 @@ int desco_partition_fill(const int32_t* rowptr, const int32_t* col, const int32_
                          const int32_t* node_off, const int32_t* edge_off, int32_t* node_gid, int32_t* edge_ptr,
                          int32_t* edge_col, uint8_t* edge_tri, int32_t* status, void* stream);
 
+/* Large-graph variants of passes 1 and 3 (config 5: a 10M-node / 200M-directed-edge target, whose node bitsets no
+ * longer fit shared memory; desco_partition_count returns DESCO_ERANGE there).  Same outputs, same reference
+ * semantics (data.py:329-396).  The set state of a centre is a hash set + member list: tier 0 in shared memory,
+ * tier 1 (balls that overflow it) in a per-CTA slice of `workspace`, and a dense bitset tier for balls that overflow
+ * that too.  The SAME workspace (desco_partition_large_workspace_bytes) must be passed to count and to fill,
+ * untouched in between: it carries the tier of every centre.  fill also runs the SHMP typing of the whole batch
+ * (num_rows = totals[1]). */
+int64_t desco_partition_large_workspace_bytes(int32_t max_graph_nodes, int32_t num_centres);
+int desco_partition_large_count(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
+                                const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
+                                int32_t max_graph_nodes, int32_t* out_nv, int32_t* out_ne, int32_t* out_centre_graph,
+                                int32_t* status, void* workspace, int64_t workspace_bytes, void* stream);
+int desco_partition_large_fill(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
+                               const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
+                               int32_t max_graph_nodes, const int32_t* nv, const int32_t* ne, const int32_t* centre_graph,
+                               const int32_t* node_off, const int32_t* edge_off, int32_t num_rows, int32_t* node_gid,
+                               int32_t* edge_ptr, int32_t* edge_col, uint8_t* edge_tri, int32_t* status, void* workspace,
+                               int64_t workspace_bytes, void* stream);
+/* Capacities of tier 0 / tier 1 (hash slots as log2, member-list entries, reached-list entries = power of two).
+ * Defaults 13/5120/4096 and 19/262144/262144; the tests shrink them to force every tier on small graphs. */
+int desco_partition_large_set_caps(int32_t log2_slots0, int32_t members0, int32_t reached0, int32_t log2_slots1,
+                                   int32_t members1, int32_t reached1);
+
 /* SHMP typing of an already-built batch / query set (ToTconvHetero applied to existing graphs, transforms.py:180-255;
  * also used for the query graphs, lightning_model.py:84-85).  Rows must have ascending edge_col. */
 int desco_shmp_edge_types(const int32_t* edge_ptr, const int32_t* edge_col, int32_t num_rows, uint8_t* edge_tri,
@@ -177,6 +200,70 @@ int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_
                          int32_t num_queries, const float* query_emb, const float* w_gossip,
                          const float* w_gossip_query, float* out, float* out_gates, void* workspace,
                          int64_t workspace_bytes, int32_t precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step of the neighborhood-counting model (BASELINE config 3)
+ * Replaces: NeighborhoodCountingModel.train_forward (lightning_model.py:228-254), criterion (:285-289),
+ *           configure_optimizers / torch.optim.Adam (:160-173) and the autograd graph through gnn_model.py:58-109,
+ *           230-277, 362-404.  fp32.  The host side (desco_b200/training.py) sequences these primitives; parameters stay
+ *           in their torch layout ([out][in] row-major) and gradients are accumulated (+=) straight into .grad buffers.
+ * Node features live per node type in compact matrices: count rows [Vc, .] (all rows for single-type query graphs),
+ * canonical rows [G, .]; compact count row of packed row r in neighborhood g is r - g.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* row_nbh[V]: packed row -> neighborhood; crow_nbh[Vc]: compact count row -> neighborhood; quirk_row[G]: the packed
+ * row whose edge to the canonical node SAGEConv's remove_self_loops drops (gnn_model.py:389-390), or -1. */
+int desco_train_plan(const int32_t* nbh_ptr, int32_t num_neighborhoods, int32_t hetero, int32_t pyg_batch_size,
+                     int32_t* row_nbh, int32_t* crow_nbh, int32_t* quirk_row, void* stream);
+
+/* transpose = 0: SAGEConv sum-aggregation (gnn_model.py:392), split by relation:
+ *   ac[count row][slot*64..] = sum of x over its neighbours of (source type, SHMP type) = slot,
+ *   slot = 2*(source is canonical) + (tride ? 1 : 0)  (4 slots hetero, 2 otherwise);  aa[g][slot*64..], slot = tride.
+ * transpose = 1: the adjoint: xc / xa += gathered ac / aa (the edge set and the types are symmetric). */
+int desco_train_aggregate(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col,
+                          const uint8_t* edge_tri, const int32_t* row_nbh, const int32_t* quirk_row, int32_t num_rows,
+                          int32_t hetero, int32_t transpose, float* xc, int32_t ldc, float* xa, int32_t lda, float* ac,
+                          int32_t ld_ac, float* aa, int32_t ld_aa, void* stream);
+
+/* y[m, n] (+)= act( sum_b x[b][m, 0:64] . W_b^T + sum_i bias[i] ).  x, ldx, w, ldw, bias are HOST arrays of device
+ * pointers / strides, one entry per 64-wide K block (<= 12) / bias (<= 4).  w_nmajor = 1: W_b[n*ldw + k] (a torch
+ * Linear weight, forward);  0: W_b[k*ldw + n] (the same weight used for the data gradient).  act: 0 none, 1 relu,
+ * 2 leaky(slope).  accumulate = 1 adds to y (act must be 0).  n % 64 == 0. */
+int desco_train_dense(const float* const* x, const int32_t* ldx, const float* const* w, const int32_t* ldw,
+                      int32_t num_blocks, int32_t w_nmajor, const float* const* bias, int32_t num_bias, float* y,
+                      int32_t ldy, int32_t m, int32_t n, int32_t act, float slope, int32_t accumulate, void* stream);
+
+/* dw[b][n*ldw[b] + k] += sum_m dy[m][n] x[m][64 b + k]  (b < num_blocks);  db[i][n] += sum_m dy[m][n]  (i < num_db). */
+int desco_train_wgrad(const float* x, int32_t ldx, int32_t num_blocks, const float* dy, int32_t ldy, int32_t n, int32_t m,
+                      float* const* dw, const int32_t* ldw, float* const* db, int32_t num_db, void* stream);
+
+/* dx[m][c] *= act'(fwd[m][c]), derivative read off the activation output (act 1 relu, 2 leaky(slope)). */
+int desco_train_act_backward(float* dx, int32_t ldd, const float* fwd, int32_t ldf, int32_t m, int32_t c, int32_t act,
+                             float slope, void* stream);
+/* y[m][0:c] = bias (pre_mp on ZeroNodeFeat inputs);  db[0:c] += column sums of dy. */
+int desco_train_fill_rows(float* y, int32_t ldy, int32_t m, int32_t c, const float* bias, void* stream);
+int desco_train_colsum(const float* dy, int32_t ldy, int32_t m, int32_t c, float* db, void* stream);
+
+/* backward = 0: pooled[g] = sum of the count rows of g (+ z_a[g] if not NULL)   (global_add_pool, gnn_model.py:107);
+ * backward = 1: emb_c[row] = pooled[neighborhood of row]  (pooled holds the gradient). */
+int desco_train_pool(const int32_t* nbh_ptr, const int32_t* crow_nbh, int32_t num_neighborhoods, int32_t num_count_rows,
+                     int32_t hetero, int32_t c, int32_t backward, float* emb_c, int32_t ldc, const float* z_a,
+                     int32_t lda, float* pooled, int32_t ldp, void* stream);
+
+/* Count head on T = t.W1[:, :64]^T [G,256] and Bq = q.W1[:, 64:]^T + b1 [Q,256] (Q <= 32):
+ *   pred[g,q] = w2 . leaky_0.01(T[g] + Bq[q]) + b2;  with y != NULL also the training loss
+ *   loss += mean_q mean_g smooth_l1(pred, log2(y + 1)) and dpred = d loss / d pred. */
+int desco_train_head_loss(const float* t, const float* bq, const float* w2, const float* b2, const float* y,
+                          int32_t num_neighborhoods, int32_t num_queries, float* pred, float* dpred, float* loss,
+                          void* stream);
+/* dt[G,256] = d loss / d T (written);  dbq[Q,256], dw2[256], db2[1] += their gradients. */
+int desco_train_head_backward(const float* t, const float* bq, const float* w2, const float* dpred,
+                              int32_t num_neighborhoods, int32_t num_queries, float* dt, float* dbq, float* dw2,
+                              float* db2, void* stream);
+
+/* torch.optim.Adam step (no amsgrad) over a flat fp32 buffer; step counts from 1. */
+int desco_train_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int32_t step, void* stream);
 
 /* Phase profile of the fused SHMP layer kernel (measurement support, no reference counterpart): clock64 cycles summed
  * over all CTAs since the last reset, as seen by thread 0 of each CTA.  out[7] = {tile setup, pool + canonical inputs,

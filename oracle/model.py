@@ -237,6 +237,18 @@ class NeighborhoodCountingModel(nn.Module):
     def graph_to_count(self, batch, query_batch, pyg_batch_size=None, self_loop_quirk=True):
         return 2 ** self.pre_exponent(batch, query_batch, pyg_batch_size, self_loop_quirk) - 1  # :221
 
+    def train_forward(self, batch, query_batch, y, pyg_batch_size=None, self_loop_quirk=True):
+        """``lightning_model.py:228-254``: per query ``criterion(results, log2(truth + 1))`` with
+        ``criterion = F.smooth_l1_loss`` (:285-289), then the mean of the stacked per-query losses."""
+        emb_q = self.get_query_emb(query_batch)
+        emb_t = self.graph_to_embed(batch, pyg_batch_size, self_loop_quirk)
+        losses = []
+        for i, q in enumerate(emb_q):
+            results = self.count_model(torch.cat((emb_t, q.expand_as(emb_t)), dim=-1))
+            truth = y[:, i].view(-1, 1)
+            losses.append(F.smooth_l1_loss(results, torch.log2(truth + 1)))
+        return torch.mean(torch.stack(losses))
+
 
 # ---------------------------------------------------------------------------------------------
 # gossip

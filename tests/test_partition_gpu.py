@@ -13,12 +13,29 @@ pytestmark = pytest.mark.gpu
 KEYS = ("nbh_ptr", "node_gid", "edge_ptr", "edge_col", "edge_tri", "centre", "index", "indicator")
 
 
-def _gpu_partition(csr, depth, mode, centres=None):
+def _gpu_partition(csr, depth, mode, centres=None, large=None):
     from desco_b200.data import DeviceCSR, partition_batch
 
     d = DeviceCSR.from_host(csr)
     c = None if centres is None else torch.as_tensor(centres, dtype=torch.int32, device=d.rowptr.device)
-    return partition_batch(d, c, depth, mode).to_numpy()
+    return partition_batch(d, c, depth, mode, large=large).to_numpy()
+
+
+DEFAULT_CAPS = (13, 5120, 4096, 19, 1 << 18, 1 << 18)
+
+
+@pytest.fixture
+def large_caps():
+    """Shrink / restore the tier capacities of the large-graph partition (so small graphs exercise every tier)."""
+    from desco_b200 import _lib
+
+    lib = _lib.load()
+
+    def set_caps(*caps):
+        _lib.check(lib.desco_partition_large_set_caps(*caps), "desco_partition_large_set_caps")
+
+    yield set_caps
+    set_caps(*DEFAULT_CAPS)
 
 
 @pytest.mark.parametrize("name", ["kat", "mutag24", "enzymes12", "imdb6"])
@@ -120,3 +137,69 @@ def test_drop_in_single_centre_api(cuda_device):
         assert sorted(a.nodes) == sorted(b.nodes)
         assert sorted(D.k_neigh(G4, 9, k)) == sorted(P.k_neigh(G4, 9, k))
     assert sorted(D.get_neigh_hetero(G4, 0, 4).nodes) == [0]
+
+
+# ---------------------------------------------------------------------------------------------
+# large-graph regime (config 5): sparse hash-set tiers + dense global-bitset tier
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["kat", "mutag24", "enzymes12", "imdb6"])
+@pytest.mark.parametrize("mode", ["hetero", "canonical"])
+def test_large_path_matches_reference_golden(cuda_device, golden_dir, name, mode):
+    z = np.load(os.path.join(golden_dir, f"partition_{name}.npz"))
+    csr = TargetCSR(z["rowptr"], z["col"], z["graph_ptr"])
+    for depth in (1, 2, 3, 4):
+        b = _gpu_partition(csr, depth, mode, large=True)
+        for k in KEYS:
+            assert np.array_equal(b[k], z[f"{mode}_d{depth}_{k}"]), (name, mode, depth, k)
+
+
+@pytest.mark.parametrize("caps,label", [
+    (DEFAULT_CAPS, "tier0"),
+    ((9, 16, 8, 12, 512, 256), "tier0+1"),        # tier 0 holds 16 members / 8 rows: most centres spill to tier 1
+    ((9, 16, 8, 9, 24, 16), "tier0+1+dense"),     # tier 1 is tiny too: the larger balls reach the dense bitset tier
+])
+def test_large_path_every_tier_matches_oracle(cuda_device, large_caps, caps, label):
+    from oracle import partition as P
+
+    large_caps(*caps)
+    for gen, kw in ((gen_enzymes_shaped, dict(num_graphs=40)), (gen_imdb_shaped, dict(num_graphs=25))):
+        csr = gen(seed=3, **kw)
+        for mode in ("hetero", "canonical"):
+            ref = P.partition_dataset(csr, 4, mode=mode)
+            b = _gpu_partition(csr, 4, mode, large=True)
+            for k in KEYS:
+                assert np.array_equal(b[k], ref[k]), (label, gen.__name__, mode, k)
+
+
+def test_large_path_powerlaw_sample_matches_oracle(cuda_device, large_caps):
+    """Config-5-shaped target (power law, hubs, random labels), depths 2 and 3, default and shrunken tiers; also the
+    plain k-hop ball (k_neigh)."""
+    from oracle import partition as P
+
+    from desco_b200.graph import gen_powerlaw
+
+    csr = gen_powerlaw(30000, 150000, seed=2)
+    rng = np.random.default_rng(1)
+    centres = np.sort(rng.choice(csr.num_nodes, size=64, replace=False)).astype(np.int32)
+    for caps in (DEFAULT_CAPS, (10, 512, 256, 15, 16384, 8192)):
+        large_caps(*caps)
+        for depth in (2, 3):
+            ref = P.partition_dataset(csr, depth, mode="hetero", centres=centres)
+            b = _gpu_partition(csr, depth, "hetero", centres, large=True)
+            for k in KEYS:
+                assert np.array_equal(b[k], ref[k]), (caps, depth, k)
+    small = _gpu_partition(csr, 2, "khop", centres[:16], large=False)
+    big = _gpu_partition(csr, 2, "khop", centres[:16], large=True)
+    for k in KEYS:
+        assert np.array_equal(small[k], big[k]), k
+
+
+def test_large_path_equals_bitset_path_full_sweep(cuda_device):
+    """Every centre of a 20k-node power-law target, depth 2: the sparse tiers and the shared-memory bitset kernel agree."""
+    from desco_b200.graph import gen_powerlaw
+
+    csr = gen_powerlaw(20000, 100000, seed=5)
+    a = _gpu_partition(csr, 2, "hetero", large=False)
+    b = _gpu_partition(csr, 2, "hetero", large=True)
+    for k in KEYS:
+        assert np.array_equal(a[k], b[k]), k
