@@ -102,15 +102,16 @@ def test_train_large_neighborhoods_and_quirk(cuda_device):
 
 
 def test_adam_steps_match_torch_adam(cuda_device):
-    """Three optimisation steps: FusedAdam on the product model vs torch.optim.Adam on the oracle (lr 1e-3 to make the
-    updates visible); parameters stay within 2e-5 relative of each other and the loss goes down on both."""
+    """Three optimisation steps at the reference's lr (1e-4, lightning_model.py:160-163): FusedAdam on the product
+    model vs torch.optim.Adam on the oracle; the loss trajectories coincide, go down, and the parameters stay within 5 %
+    of one step's update of each other."""
     from oracle import model as M
 
     om, pm, b_np, batch, y = _setup(gen_mutag_shaped(seed=5, num_graphs=16), seed=1)
-    pm.lr = 1e-3
+    pm.lr = 1e-4
     cfg = pm.configure_optimizers()
     opt = cfg["optimizer"]
-    ref_opt = torch.optim.Adam(om.parameters(), lr=1e-3, weight_decay=0.0)
+    ref_opt = torch.optim.Adam(om.parameters(), lr=1e-4, weight_decay=0.0)
     qb = M.query_batch()
     losses, ref_losses = [], []
     for step in range(3):
@@ -126,13 +127,13 @@ def test_adam_steps_match_torch_adam(cuda_device):
         ref_losses.append(rl.item())
     assert losses[-1] < losses[0] and ref_losses[-1] < ref_losses[0]
     for a, b in zip(losses, ref_losses):
-        assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (losses, ref_losses)
+        assert abs(a - b) <= 2e-4 * max(1.0, abs(b)), (losses, ref_losses)
     ref = dict(om.named_parameters())
     for name, p in pm.named_parameters():
         r = ref[name].detach()
         d = (p.detach().cpu() - r).abs().max().item()
         # Adam normalises the update to ~lr per step whatever the gradient scale, so compare on the lr scale
-        assert d <= 3 * 1e-3 * 0.05, f"{name}: parameter drift {d}"
+        assert d <= 3 * 1e-4 * 0.1, f"{name}: parameter drift {d}"
 
 
 def test_training_then_inference_uses_new_weights(cuda_device):
