@@ -201,19 +201,16 @@ __global__ void __launch_bounds__(256) partition_kernel(
     // fill pass inputs / outputs (fill == 1)
     int fill, const int32_t* __restrict__ node_off, const int32_t* __restrict__ edge_off,
     int32_t* __restrict__ node_gid, int32_t* __restrict__ edge_ptr, int32_t* __restrict__ edge_col,
-    uint8_t* __restrict__ edge_tri, int32_t* __restrict__ status,
-    // dense tier of the large-graph path: bitsets in a per-CTA slice of global scratch, only centres of class `klass_want`
-    uint32_t* __restrict__ gscratch = nullptr, const uint8_t* __restrict__ klass = nullptr, int klass_want = 0) {
+    uint8_t* __restrict__ edge_tri, int32_t* __restrict__ status) {
   extern __shared__ uint32_t smem[];
   const int groups_per_cta = CTA ? 1 : (blockDim.x >> 5);
   const int g_in_cta = CTA ? 0 : warp_id();
-  uint32_t* S = gscratch ? gscratch + (size_t)blockIdx.x * 4 * max_words : smem + (size_t)g_in_cta * 4 * max_words;
+  uint32_t* S = smem + (size_t)g_in_cta * 4 * max_words;
   uint32_t* F = S + max_words;
   uint32_t* Nx = F + max_words;
   uint32_t* aux = Nx + max_words;
 
   for (int ci = blockIdx.x * groups_per_cta + g_in_cta; ci < num_centres; ci += gridDim.x * groups_per_cta) {
-    if (klass && klass[ci] != klass_want) continue;
     const int centre = centres[ci];
     int gid;
     if (fill) {
@@ -323,7 +320,7 @@ __global__ void __launch_bounds__(256) partition_kernel(
           if (v > limit) break;
           if (!bit_test(S, v - lo)) continue;
           edge_col[out] = n0 + local_index(S, pref, v - lo);
-          edge_tri[out] = (gscratch == nullptr && has_common_neighbour(rowptr, col, S, lo, limit, u, v)) ? 1 : 0;
+          edge_tri[out] = has_common_neighbour(rowptr, col, S, lo, limit, u, v) ? 1 : 0;
           ++out;
         }
         ++k;
@@ -618,15 +615,15 @@ __global__ void edge_types_kernel(const int32_t* __restrict__ edge_ptr, const in
 
 // ------------------------------------------------------------------------------------------------------------------
 // Large-graph regime (config 5: one 10M-node / 200M-directed-edge power-law target).  A bitset over the target no
-// longer fits shared memory and would cost O(N/32) per centre, so the set state of a centre is SPARSE:
+// longer fits shared memory and would cost O(N/32) per centre, so the set state of an ordinary centre is SPARSE and
+// lives in shared memory (tier 0):
 //   * an open-addressing hash set of node ids (linear probing, atomicCAS insert; bit 31 of a key = "reached" flag),
 //   * the member list L in discovery order (BFS levels are contiguous slices of it),
 //   * the reached list R (component of the centre), bitonic-sorted at the end so that rows come out in ascending node
 //     id and a local id is a binary search.
-// Tier 0 keeps all three in shared memory; a centre whose ball overflows them is re-run by tier 1 (same code, tables in
-// a per-CTA slice of global scratch, L2-resident), and a ball that overflows that too by the dense tier (the bitset
-// kernel above with its four bitsets in global scratch).  The sorted adjacency makes "<= centre" a PREFIX of every
-// row, so the restricted passes stop at the first neighbour above the centre.
+// A centre whose ball overflows these tables is appended to the big-centre list and served by the team tier below.
+// The sorted adjacency makes "<= centre" a PREFIX of every row, so the restricted passes stop at the first neighbour
+// above the centre.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t SP_EMPTY = 0xffffffffu;
 constexpr uint32_t SP_FLAG = 0x80000000u;
@@ -639,8 +636,8 @@ struct SparseArgs {
   int32_t* out_nv; int32_t* out_ne; int32_t* centre_graph;
   int fill; const int32_t* node_off; const int32_t* edge_off;
   int32_t* node_gid; int32_t* edge_ptr; int32_t* edge_col;
-  uint8_t* klass; int tier;      // centre class: 0 = tier 0 (shared memory), 1 = tier 1 (global scratch), 2 = dense tier
-  uint32_t* gscratch;            // tier 1: per-CTA slice of (H + capL + capR) words
+  uint8_t* klass; int tier;      // centre class: 0 = served by this kernel (shared memory), 1 = handed to the team tier
+  int32_t* big_list; int* big_count;  // centres handed to the team tier (appended by the count pass)
   int log2H, capL, capR;         // hash slots (power of two), member-list / reached-list capacities (capR power of two)
 };
 
@@ -688,13 +685,12 @@ struct SparseSet {
   }
 };
 
-template <bool GLOBAL>
 __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const SparseArgs p) {
   extern __shared__ uint32_t sp_smem[];
   __shared__ int s_nL, s_nR, s_over, s_cnt, s_gid;
   SparseSet set;
   set.log2H = p.log2H; set.H = 1 << p.log2H; set.capL = p.capL; set.capR = p.capR;
-  set.keys = GLOBAL ? p.gscratch + (size_t)blockIdx.x * ((size_t)set.H + p.capL + p.capR) : sp_smem;
+  set.keys = sp_smem;
   set.L = set.keys + set.H;
   set.R = set.L + p.capL;
   set.nL = &s_nL; set.nR = &s_nR; set.over = &s_over;
@@ -703,14 +699,10 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
   const int32_t* __restrict__ rowptr = p.rowptr;
   const int32_t* __restrict__ col = p.col;
 
-  bool table_ready = false;  // tier 1 wipes its 2 MB table only if it really owns a centre
+  bool table_ready = false;
 
   for (int ci = blockIdx.x; ci < p.num_centres; ci += gridDim.x) {
-    if (p.fill) {
-      if (p.klass[ci] != p.tier || p.out_ne[ci] == 0) continue;
-    } else if (p.tier != 0 && p.klass[ci] != p.tier) {
-      continue;
-    }
+    if (p.fill && (p.klass[ci] != 0 || p.out_ne[ci] == 0)) continue;
     if (!table_ready) {
       for (int i = tid; i < set.H; i += SP_THREADS) set.keys[i] = SP_EMPTY;
       table_ready = true;
@@ -809,12 +801,13 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
     }
 
     if (over) {
-      // this tier cannot hold the ball: hand the centre to the next tier and wipe the table
+      // shared memory cannot hold the ball: hand the centre to the team tier and wipe the table
       if (tid == 0 && !p.fill) {
-        p.klass[ci] = (uint8_t)(p.tier + 1);
+        p.klass[ci] = 1;
         p.out_nv[ci] = 0;
         p.out_ne[ci] = 0;
         p.centre_graph[ci] = s_gid;
+        p.big_list[atomicAdd(p.big_count, 1)] = ci;
       }
       __syncthreads();
       for (int i = tid; i < set.H; i += SP_THREADS) set.keys[i] = SP_EMPTY;
@@ -875,7 +868,7 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
         p.out_ne[ci] = ne;
         p.out_nv[ci] = ne > 0 ? nv : 0;  // edge-free neighborhoods are dropped (workload.py:253-256)
         p.centre_graph[ci] = s_gid;
-        if (p.tier == 0) p.klass[ci] = 0;
+        p.klass[ci] = 0;
       }
     } else {
       if (n0 == 0 && tid == 0) p.edge_ptr[0] = 0;
@@ -907,41 +900,409 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
     }
     __syncthreads();
 
-    // ---- wipe the table: tier 0 clears all slots, tier 1 only the members' ----
-    if (!GLOBAL || s_nL > set.H / 16) {
-      for (int i = tid; i < set.H; i += SP_THREADS) set.keys[i] = SP_EMPTY;
-    } else {
-      const int n = s_nL;
-      for (int i = tid; i < n; i += SP_THREADS) set.L[i] = (uint32_t)set.find((int)set.L[i]);
-      __syncthreads();
-      for (int i = tid; i < n; i += SP_THREADS) set.keys[set.L[i]] = SP_EMPTY;
-    }
+    // ---- wipe the table ----
+    for (int i = tid; i < set.H; i += SP_THREADS) set.keys[i] = SP_EMPTY;
     __syncthreads();
   }
 }
 
-// tunables of the large-graph path (desco_partition_large_set_caps lets the tests force every tier on small graphs)
+// ------------------------------------------------------------------------------------------------------------------
+// Team tier: balls that overflow the shared-memory tier (a few per cent of the centres of a power-law target, but most
+// of its rows: a hub's depth-2 ball has 10^5..10^6 rows).  One CTA per such centre leaves ~256 L2 requests in flight for
+// millions of adjacency probes, so a TEAM of TM_CTAS co-resident CTAs (cooperative launch) owns the centre instead:
+//   * member set and reached set are BITMAPS over the centre's target graph in a per-team slice of global scratch
+//     (L2-resident: 1.25 MB per set for 10M nodes); a reached word is a {bits, prefix} pair, so "is v in the
+//     neighborhood" and "local id of v" are ONE 8-byte load, and ascending-node-id order needs no sort;
+//   * frontier / reached nodes are appended to lists (warp-aggregated atomics), BFS levels are slices of the list;
+//   * phases are separated by a team barrier (arrive counter + generation in global memory); the last arriver
+//     snapshots the list lengths, so every CTA leaves the barrier with the same view;
+//   * adjacency rows are streamed a warp per row, or - while a level has fewer rows than the team has warps (level 0 is
+//     the centre alone, possibly a hub) - 32-entry chunks of each row dealt over all warps of the team.
+// Big centres are taken from a list the tier-0 kernel appends to, through an atomic ticket (dynamic balancing).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TM_THREADS = 256;
+constexpr int TM_CTAS = 16;
+constexpr int TM_WARPS = TM_THREADS / 32;
+
+struct TeamCtrl {
+  unsigned bar_count, bar_gen;
+  int cur[2];          // ticket (index into big_list) of the centre of this / the next iteration (by parity)
+  int nL, nR, cnt;     // member-list length, reached-list length, induced directed edges
+  int abort;
+  int snap[2][4];      // barrier snapshot (nL, nR, cnt, abort) by generation parity
+  int chunk_tot[TM_CTAS];
+  int pad[4];
+};
+static_assert(sizeof(TeamCtrl) % 16 == 0, "TeamCtrl must keep the slices aligned");
+
+struct TeamArgs {
+  const int32_t* rowptr; const int32_t* col; const int32_t* graph_ptr; int num_graphs;
+  const int32_t* centres; int num_centres, depth, mode;
+  int32_t* out_nv; int32_t* out_ne; int32_t* centre_graph;
+  int fill; const int32_t* node_off; const int32_t* edge_off;
+  int32_t* node_gid; int32_t* edge_ptr; int32_t* edge_col;
+  const int32_t* big_list; int* big_count; int* ticket;
+  TeamCtrl* ctrl; uint8_t* slices; size_t slice_bytes;
+  int max_words, max_nodes;
+  int32_t* status;
+};
+
+struct TeamSnap { int nL, nR, cnt, abort; };
+
+__device__ __forceinline__ TeamSnap team_sync(TeamCtrl* c, int* s_snap) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned gen = *reinterpret_cast<volatile unsigned*>(&c->bar_gen);
+    const int par = (int)(gen & 1u);
+    if (atomicAdd(&c->bar_count, 1u) == (unsigned)(TM_CTAS - 1)) {
+      c->snap[par][0] = __ldcg(&c->nL);
+      c->snap[par][1] = __ldcg(&c->nR);
+      c->snap[par][2] = __ldcg(&c->cnt);
+      c->snap[par][3] = __ldcg(&c->abort);
+      *reinterpret_cast<volatile unsigned*>(&c->bar_count) = 0u;
+      __threadfence();
+      atomicAdd(&c->bar_gen, 1u);
+    } else {
+      bool ok = false;  // bounded: a lost team-mate must never hang the GPU box
+      for (unsigned spin = 0; spin < (1u << 23); ++spin) {
+        if (*reinterpret_cast<volatile unsigned*>(&c->bar_gen) != gen) { ok = true; break; }
+        __nanosleep(40);
+      }
+      if (!ok) atomicExch(&c->abort, 1);
+    }
+    __threadfence();
+    s_snap[0] = __ldcg(&c->snap[par][0]);
+    s_snap[1] = __ldcg(&c->snap[par][1]);
+    s_snap[2] = __ldcg(&c->snap[par][2]);
+    s_snap[3] = __ldcg(&c->snap[par][3]) | __ldcg(&c->abort);
+  }
+  __syncthreads();
+  TeamSnap r;
+  r.nL = s_snap[0]; r.nR = s_snap[1]; r.cnt = s_snap[2]; r.abort = s_snap[3];
+  return r;
+}
+
+// f(v, ok) is called warp-uniformly for 32 adjacency entries at a time of every node of list[lb, le); ok = the entry
+// exists and is <= limit (rows are sorted, so a warp stops a row at its first failing chunk).
+template <typename Fn>
+__device__ __forceinline__ void team_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                          const int32_t* list, int lb, int le, int limit, int rank, Fn f) {
+  const int lane = lane_id();
+  const int gw = rank * TM_WARPS + warp_id();
+  constexpr int TW = TM_CTAS * TM_WARPS;
+  if (le - lb >= TW) {
+    for (int i = lb + gw; i < le; i += TW) {
+      const int u = __ldcg(list + i);
+      const int rb = rowptr[u], re = rowptr[u + 1];
+      for (int e0 = rb; e0 < re; e0 += 32) {
+        const int e = e0 + lane;
+        const int v = (e < re) ? col[e] : 0;
+        const bool ok = e < re && v <= limit;
+        f(v, ok);
+        if (!__all_sync(FULL_MASK, ok)) break;
+      }
+    }
+  } else {
+    for (int i = lb; i < le; ++i) {
+      const int u = __ldcg(list + i);
+      const int rb = rowptr[u], re = rowptr[u + 1];
+      for (int e0 = rb + gw * 32; e0 < re; e0 += TW * 32) {
+        const int e = e0 + lane;
+        const int v = (e < re) ? col[e] : 0;
+        const bool ok = e < re && v <= limit;
+        f(v, ok);
+        if (!__all_sync(FULL_MASK, ok)) break;
+      }
+    }
+  }
+}
+
+// warp-aggregated append of the lanes with `take` set
+__device__ __forceinline__ void team_append(int32_t* list, int* counter, int cap, int v, bool take) {
+  const uint32_t m = __ballot_sync(FULL_MASK, take);
+  if (!m) return;
+  int base = 0;
+  if (lane_id() == 0) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(FULL_MASK, base, 0);
+  const int idx = base + __popc(m & ((1u << lane_id()) - 1u));
+  if (take && idx < cap) list[idx] = v;
+}
+
+__global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamArgs p) {
+  __shared__ int s_snap[4];
+  __shared__ int s_wtot[TM_WARPS];
+  __shared__ int s_gid;
+  const int team = blockIdx.x / TM_CTAS, rank = blockIdx.x % TM_CTAS;
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  constexpr int TT = TM_CTAS * TM_THREADS;
+  const int tt = rank * TM_THREADS + tid;
+  TeamCtrl* c = p.ctrl + team;
+  uint8_t* slice = p.slices + (size_t)team * p.slice_bytes;
+  uint2* RP = reinterpret_cast<uint2*>(slice);                                 // [max_words] {reached bits, prefix}
+  uint32_t* Mb = reinterpret_cast<uint32_t*>(slice + (size_t)p.max_words * 8); // [max_words] member bits
+  int32_t* L = reinterpret_cast<int32_t*>(slice + (size_t)p.max_words * 12);   // [max_nodes] members, discovery order
+  int32_t* R = L + p.max_nodes;                                                // [max_nodes] reached, discovery order
+  const int32_t* __restrict__ rowptr = p.rowptr;
+  const int32_t* __restrict__ col = p.col;
+  const int nbig = __ldcg(p.big_count);
+
+  if (rank == 0 && tid == 0) c->cur[0] = atomicAdd(p.ticket, 1);
+  TeamSnap sn = team_sync(c, s_snap);
+  for (int iter = 0; !sn.abort; ++iter) {
+    // two slots: an iteration without inner barriers (dropped centre) must not overwrite the ticket the slower
+    // team-mates are still about to read
+    const int item = __ldcg(&c->cur[iter & 1]);
+    if (item >= nbig) break;
+    const int ci = __ldcg(p.big_list + item);
+    const int centre = p.centres[ci];
+    const bool skip = p.fill && p.out_ne[ci] == 0;  // dropped neighborhood: nothing to emit
+    if (tid == 0) {
+      int a = 0, b = p.num_graphs;  // largest a with graph_ptr[a] <= centre
+      while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (p.graph_ptr[mid] <= centre) a = mid; else b = mid;
+      }
+      s_gid = a;
+    }
+    __syncthreads();
+    const int gid = s_gid;
+    const int lo = p.graph_ptr[gid];
+    const int W = (p.graph_ptr[gid + 1] - lo + 31) >> 5;
+    const int limit = (p.mode == DESCO_MODE_KHOP) ? 0x7fffffff : centre;
+    const int cl = centre - lo;
+    if (W > p.max_words) {
+      if (rank == 0 && tid == 0) {
+        atomicExch(p.status, DESCO_ERANGE);
+        if (!p.fill) { p.out_nv[ci] = 0; p.out_ne[ci] = 0; p.centre_graph[ci] = gid; }
+      }
+    } else if (!skip) {
+      if (rank == 0 && tid == 0) {
+        Mb[cl >> 5] = 1u << (cl & 31);
+        L[0] = centre;
+        c->nL = 1; c->nR = 0; c->cnt = 0;
+      }
+      sn = team_sync(c, s_snap);
+      if (sn.abort) break;
+
+      // ---- phase A: k levels of frontier expansion (data.py:329-350) ----
+      int lb = 0, le = 1;
+      for (int level = 0; level < p.depth && lb < le; ++level) {
+        const bool restricted = p.mode == DESCO_MODE_CANONICAL || (p.mode == DESCO_MODE_HETERO && level == p.depth - 1);
+        team_rows(rowptr, col, L, lb, le, restricted ? centre : 0x7fffffff, rank, [&](int v, bool ok) {
+          bool take = false;
+          if (ok) {
+            const int i = v - lo;
+            const uint32_t bit = 1u << (i & 31);
+            if (!(__ldcg(Mb + (i >> 5)) & bit)) take = !(atomicOr(Mb + (i >> 5), bit) & bit);
+          }
+          team_append(L, &c->nL, p.max_nodes, v, take);
+        });
+        sn = team_sync(c, s_snap);
+        lb = le;
+        le = min(sn.nL, p.max_nodes);
+      }
+      const int nL = min(sn.nL, p.max_nodes);
+
+      // ---- phase B + C: candidates <= centre (data.py:385), component of the centre inside them (:387-390) ----
+      if (p.mode == DESCO_MODE_HETERO) {
+        if (rank == 0 && tid == 0) {
+          RP[cl >> 5].x = 1u << (cl & 31);
+          R[0] = centre;
+          c->nR = 1;
+        }
+        sn = team_sync(c, s_snap);
+        int qb = 0, qe = 1;
+        while (qb < qe && !sn.abort) {
+          team_rows(rowptr, col, R, qb, qe, centre, rank, [&](int v, bool ok) {
+            bool take = false;
+            if (ok) {
+              const int i = v - lo;
+              const uint32_t bit = 1u << (i & 31);
+              if ((__ldcg(Mb + (i >> 5)) & bit) && !(__ldcg(&RP[i >> 5].x) & bit))
+                take = !(atomicOr(&RP[i >> 5].x, bit) & bit);
+            }
+            team_append(R, &c->nR, p.max_nodes, v, take);
+          });
+          sn = team_sync(c, s_snap);
+          qb = qe;
+          qe = min(sn.nR, p.max_nodes);
+        }
+      } else {  // restricted BFS / plain k-hop ball: every member is in the result
+        for (int i = tt; i < nL; i += TT) {
+          const int v = __ldcg(L + i);
+          R[i] = v;
+          atomicOr(&RP[(v - lo) >> 5].x, 1u << ((v - lo) & 31));
+        }
+        if (rank == 0 && tid == 0) c->nR = nL;
+        sn = team_sync(c, s_snap);
+      }
+      if (sn.abort) break;
+      const int nv = min(sn.nR, p.max_nodes);
+      const int n0 = p.fill ? p.node_off[ci] : 0;
+      const int eo = p.fill ? p.edge_off[ci] : 0;
+
+      // ---- phase D: ranks = popcount prefix over the reached bitmap (ascending node id; canonical node = last row) ----
+      if (p.fill) {
+        const int wchunk = (W + TM_CTAS - 1) / TM_CTAS;               // words per CTA
+        const int wper = ((wchunk + TM_WARPS - 1) / TM_WARPS + 31) & ~31;  // words per warp, whole 32-word trips
+        const int wb = rank * wchunk + warp * wper;
+        const int we = min(min(wb + wper, (rank + 1) * wchunk), W);
+        int tot = 0;
+        for (int w0 = wb; w0 < we; w0 += 32) tot += (w0 + lane < we) ? __popc(__ldcg(&RP[w0 + lane].x)) : 0;
+        tot = warp_sum(tot);
+        if (lane == 0) s_wtot[warp] = tot;
+        __syncthreads();
+        if (tid == 0) {
+          int t = 0;
+          for (int k = 0; k < TM_WARPS; ++k) t += s_wtot[k];
+          c->chunk_tot[rank] = t;
+        }
+        sn = team_sync(c, s_snap);
+        int carry = 0;
+        for (int k = 0; k < rank; ++k) carry += __ldcg(&c->chunk_tot[k]);
+        for (int k = 0; k < warp; ++k) carry += s_wtot[k];
+        for (int w0 = wb; w0 < we; w0 += 32) {
+          const int w = w0 + lane;
+          uint32_t x = (w < we) ? __ldcg(&RP[w].x) : 0u;
+          const int cpop = __popc(x);
+          const int incl = warp_incl_scan(cpop);
+          int pre = carry + incl - cpop;
+          if (x) {
+            RP[w].y = (uint32_t)pre;
+            while (x) {
+                p.node_gid[n0 + pre++] = lo + 32 * w + __ffs(x) - 1;
+                x &= x - 1;
+              }
+          }
+          carry += __shfl_sync(FULL_MASK, incl, 31);
+        }
+        __syncthreads();  // s_wtot is reused below
+      }
+
+      if (!p.fill) {
+        // ---- induced directed edge total ----
+        int cnt = 0;
+        team_rows(rowptr, col, R, 0, nv, limit, rank, [&](int v, bool ok) {
+          if (ok) cnt += (__ldcg(&RP[(v - lo) >> 5].x) >> ((v - lo) & 31)) & 1u;
+        });
+        cnt = warp_sum(cnt);
+        if (lane == 0 && cnt) atomicAdd(&c->cnt, cnt);
+        sn = team_sync(c, s_snap);
+        if (rank == 0 && tid == 0) {
+          p.out_ne[ci] = sn.cnt;
+          p.out_nv[ci] = sn.cnt > 0 ? nv : 0;  // edge-free neighborhoods are dropped (workload.py:253-256)
+          p.centre_graph[ci] = gid;
+        }
+      } else {
+        if (n0 == 0 && rank == 0 && tid == 0) p.edge_ptr[0] = 0;
+        sn = team_sync(c, s_snap);  // node_gid of every row is in place
+        // ---- induced degree of the rows of this CTA's rank chunk (warp per row) + chunk total ----
+        const int rchunk = (nv + TM_CTAS - 1) / TM_CTAS;
+        const int rb0 = rank * rchunk, re0 = min(rb0 + rchunk, nv);
+        int wsum = 0;
+        for (int i = rb0 + warp; i < re0; i += TM_WARPS) {
+          const int u = __ldcg(p.node_gid + n0 + i);
+          const int rb = rowptr[u], re = rowptr[u + 1];
+          int cnt = 0;
+          for (int e0 = rb; e0 < re; e0 += 32) {
+            const int e = e0 + lane;
+            const int v = (e < re) ? col[e] : 0;
+            const bool ok = e < re && v <= limit;
+            if (ok) cnt += (__ldcg(&RP[(v - lo) >> 5].x) >> ((v - lo) & 31)) & 1u;
+            if (!__all_sync(FULL_MASK, ok)) break;
+          }
+          cnt = warp_sum(cnt);
+          if (lane == 0) p.edge_ptr[n0 + 1 + i] = cnt;
+          wsum += cnt;
+        }
+        if (lane == 0) s_wtot[warp] = wsum;
+        __syncthreads();
+        if (tid == 0) {
+          int t = 0;
+          for (int k = 0; k < TM_WARPS; ++k) t += s_wtot[k];
+          c->chunk_tot[rank] = t;
+        }
+        sn = team_sync(c, s_snap);
+        // ---- inclusive scan of the chunk's degrees (one warp; chunk base = totals of the lower chunks) ----
+        if (warp == 0) {
+          int carry = eo;
+          for (int k = 0; k < rank; ++k) carry += __ldcg(&c->chunk_tot[k]);
+          for (int base = rb0; base < re0; base += 32) {
+            const int x = (base + lane < re0) ? __ldcg(p.edge_ptr + n0 + 1 + base + lane) : 0;
+            const int incl = warp_incl_scan(x);
+            if (base + lane < re0) p.edge_ptr[n0 + 1 + base + lane] = carry + incl;
+            carry += __shfl_sync(FULL_MASK, incl, 31);
+          }
+        }
+        sn = team_sync(c, s_snap);
+        // ---- edges in adjacency order (ascending node id == ascending local id); types follow in edge_types_kernel ----
+        constexpr int TW = TM_CTAS * TM_WARPS;
+        for (int i = rank * TM_WARPS + warp; i < nv; i += TW) {
+          const int u = __ldcg(p.node_gid + n0 + i);
+          const int rb = rowptr[u], re = rowptr[u + 1];
+          int out = (i == 0) ? eo : __ldcg(p.edge_ptr + n0 + i);
+          for (int e0 = rb; e0 < re; e0 += 32) {
+            const int e = e0 + lane;
+            const int v = (e < re) ? col[e] : 0;
+            const bool ok = e < re && v <= limit;
+            uint2 rp = make_uint2(0u, 0u);
+            if (ok) rp = __ldcg(&RP[(v - lo) >> 5]);
+            const uint32_t bit = 1u << ((v - lo) & 31);
+            const bool in = ok && (rp.x & bit);
+            const uint32_t m = __ballot_sync(FULL_MASK, in);
+            if (in) p.edge_col[out + __popc(m & ((1u << lane) - 1u))] = n0 + (int)rp.y + __popc(rp.x & (bit - 1u));
+            out += __popc(m);
+            if (!__all_sync(FULL_MASK, ok)) break;
+          }
+        }
+        sn = team_sync(c, s_snap);  // every team-mate is done reading the reached words
+      }
+
+      // ---- wipe the words this centre touched (nobody reads the member bits after phase C) ----
+      for (int i = tt; i < nL; i += TT) Mb[(__ldcg(L + i) - lo) >> 5] = 0u;
+      for (int i = tt; i < nv; i += TT) RP[(__ldcg(R + i) - lo) >> 5] = make_uint2(0u, 0u);
+    }
+    if (rank == 0 && tid == 0) c->cur[(iter + 1) & 1] = atomicAdd(p.ticket, 1);
+    sn = team_sync(c, s_snap);
+  }
+  if (sn.abort && rank == 0 && tid == 0) atomicExch(p.status, DESCO_ECUDA);
+}
+
+// tunables of the large-graph path (desco_partition_large_set_caps lets the tests force the team tier on small graphs)
 int g_sp_log2h0 = 13, g_sp_capl0 = 5120, g_sp_capr0 = 4096;      // tier 0: 32 + 20 + 16 KB of shared memory
-int g_sp_log2h1 = 19, g_sp_capl1 = 1 << 18, g_sp_capr1 = 1 << 18;  // tier 1: 4 MB of global scratch per CTA
 
 struct LargeLayout {
-  size_t klass_off, t1_off, t2_off, bytes;
-  int t1_ctas, t2_ctas, max_words;
-  size_t t1_words;
+  size_t klass_off, counters_off, list_off, ctrl_off, slices_off, slice_bytes, bytes;
+  int teams, max_words;
 };
+
+int team_count() {  // co-resident teams: the cooperative launch needs every CTA of the grid on the device at once
+  static int teams = 0;
+  if (!teams) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, partition_team_kernel, TM_THREADS, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    teams = desco_num_sms() * per_sm / TM_CTAS;
+    if (teams < 1) teams = 1;
+  }
+  return teams;
+}
 
 LargeLayout large_layout(int max_graph_nodes, int num_centres) {
   LargeLayout l;
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const int sms = desco_num_sms();
+  const size_t nc = (size_t)(num_centres > 0 ? num_centres : 1);
+  l.teams = team_count();
   l.max_words = (max_graph_nodes + 31) / 32;
-  l.t1_ctas = 4 * sms;  // tier 1 is latency bound on L2 hash probes: four 256-thread CTAs per SM
-  l.t2_ctas = sms;
-  l.t1_words = ((size_t)1 << g_sp_log2h1) + g_sp_capl1 + g_sp_capr1;
   l.klass_off = 0;
-  l.t1_off = up((size_t)(num_centres > 0 ? num_centres : 1));
-  l.t2_off = l.t1_off + up(l.t1_words * 4 * l.t1_ctas);
-  l.bytes = l.t2_off + up((size_t)4 * l.max_words * 4 * l.t2_ctas);
+  l.counters_off = up(nc);
+  l.list_off = l.counters_off + 256;
+  l.ctrl_off = l.list_off + up(nc * 4);
+  l.slices_off = l.ctrl_off + up(sizeof(TeamCtrl) * l.teams);
+  l.slice_bytes = up((size_t)l.max_words * 12 + (size_t)max_graph_nodes * 8);
+  l.bytes = l.slices_off + l.slice_bytes * l.teams;
   return l;
 }
 
@@ -959,38 +1320,45 @@ int launch_partition_large(const int32_t* rowptr, const int32_t* col, const int3
   if ((int64_t)l.bytes > workspace_bytes) return DESCO_ENOMEM;
   uint8_t* base = (uint8_t*)workspace;
   const int sms = desco_num_sms();
+  int* counters = (int*)(base + l.counters_off);  // [0] big centres, [1] ticket
   SparseArgs a;
   a.rowptr = rowptr; a.col = col; a.graph_ptr = graph_ptr; a.num_graphs = num_graphs;
   a.centres = centres; a.num_centres = num_centres; a.depth = depth; a.mode = mode;
   a.out_nv = nv; a.out_ne = ne; a.centre_graph = centre_graph;
   a.fill = fill; a.node_off = node_off; a.edge_off = edge_off; a.node_gid = node_gid; a.edge_ptr = edge_ptr; a.edge_col = edge_col;
   a.klass = base + l.klass_off;
-  DescoProfScope prof(DESCO_PROF_PARTITION, stream, 3);
+  a.big_list = (int32_t*)(base + l.list_off); a.big_count = counters;
+  DescoProfScope prof(DESCO_PROF_PARTITION, stream, 2);
+  // the count pass builds the list of big centres; fill reuses it.  Team state (barriers, bitmaps) starts from zero.
+  if (!fill) DESCO_CUDA_TRY(cudaMemsetAsync(counters, 0, 256, stream));
+  else DESCO_CUDA_TRY(cudaMemsetAsync(counters + 1, 0, sizeof(int), stream));
+  DESCO_CUDA_TRY(cudaMemsetAsync(base + l.ctrl_off, 0, l.slices_off - l.ctrl_off, stream));
+  for (int t = 0; t < l.teams; ++t)
+    DESCO_CUDA_TRY(cudaMemsetAsync(base + l.slices_off + (size_t)t * l.slice_bytes, 0, (size_t)l.max_words * 12, stream));
   {  // tier 0: shared memory
-    a.tier = 0; a.gscratch = nullptr; a.log2H = g_sp_log2h0; a.capL = g_sp_capl0; a.capR = g_sp_capr0;
+    a.tier = 0; a.log2H = g_sp_log2h0; a.capL = g_sp_capl0; a.capR = g_sp_capr0;
     const size_t smem = (((size_t)1 << a.log2H) + a.capL + a.capR) * 4;
     if (smem > 200 * 1024) return DESCO_EINVAL;
-    DESCO_CUDA_TRY(cudaFuncSetAttribute(partition_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DESCO_CUDA_TRY(cudaFuncSetAttribute(partition_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     const int blocks = num_centres < sms * per_sm ? num_centres : sms * per_sm;
-    partition_sparse_kernel<false><<<blocks, SP_THREADS, smem, stream>>>(a);
+    partition_sparse_kernel<<<blocks, SP_THREADS, smem, stream>>>(a);
     DESCO_LAUNCH_CHECK();
   }
-  {  // tier 1: global scratch
-    a.tier = 1; a.gscratch = (uint32_t*)(base + l.t1_off); a.log2H = g_sp_log2h1; a.capL = g_sp_capl1; a.capR = g_sp_capr1;
-    const int blocks = num_centres < l.t1_ctas ? num_centres : l.t1_ctas;
-    partition_sparse_kernel<true><<<blocks, SP_THREADS, 0, stream>>>(a);
-    DESCO_LAUNCH_CHECK();
-  }
-  {  // dense tier: bitsets over the whole target graph in global scratch
-    const int blocks = num_centres < l.t2_ctas ? num_centres : l.t2_ctas;
-    partition_kernel<true><<<blocks, 256, 0, stream>>>(rowptr, col, graph_ptr, num_graphs, centres, num_centres, depth, mode,
-                                                      l.max_words, nv, ne, centre_graph, fill, node_off, edge_off, node_gid,
-                                                      edge_ptr, edge_col, edge_tri, status,
-                                                      (uint32_t*)(base + l.t2_off), a.klass, 2);
-    DESCO_LAUNCH_CHECK();
+  {  // team tier: global bitmaps, TM_CTAS co-resident CTAs per centre
+    TeamArgs t;
+    t.rowptr = rowptr; t.col = col; t.graph_ptr = graph_ptr; t.num_graphs = num_graphs;
+    t.centres = centres; t.num_centres = num_centres; t.depth = depth; t.mode = mode;
+    t.out_nv = nv; t.out_ne = ne; t.centre_graph = centre_graph;
+    t.fill = fill; t.node_off = node_off; t.edge_off = edge_off; t.node_gid = node_gid; t.edge_ptr = edge_ptr; t.edge_col = edge_col;
+    t.big_list = a.big_list; t.big_count = counters; t.ticket = counters + 1;
+    t.ctrl = (TeamCtrl*)(base + l.ctrl_off); t.slices = base + l.slices_off; t.slice_bytes = l.slice_bytes;
+    t.max_words = l.max_words; t.max_nodes = max_graph_nodes; t.status = status;
+    void* params[] = {(void*)&t};
+    DESCO_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)partition_team_kernel, dim3(l.teams * TM_CTAS), dim3(TM_THREADS),
+                                               params, 0, stream));
   }
   return DESCO_OK;
 }
@@ -1147,11 +1515,10 @@ int64_t desco_partition_large_workspace_bytes(int32_t max_graph_nodes, int32_t n
 int desco_partition_large_set_caps(int32_t log2_slots0, int32_t members0, int32_t reached0, int32_t log2_slots1,
                                    int32_t members1, int32_t reached1) {
   auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
-  if (log2_slots0 < 4 || log2_slots0 > 15 || log2_slots1 < 4 || log2_slots1 > 26 || !pow2(reached0) || !pow2(reached1) ||
-      members0 < 1 || members1 < 1 || members0 + SP_THREADS > (1 << log2_slots0) || members1 + SP_THREADS > (1 << log2_slots1))
+  (void)log2_slots1; (void)members1; (void)reached1;  // the team tier has no capacity limit (bitmaps over the target graph)
+  if (log2_slots0 < 4 || log2_slots0 > 15 || !pow2(reached0) || members0 < 1 || members0 + SP_THREADS > (1 << log2_slots0))
     return DESCO_EINVAL;
   g_sp_log2h0 = log2_slots0; g_sp_capl0 = members0; g_sp_capr0 = reached0;
-  g_sp_log2h1 = log2_slots1; g_sp_capl1 = members1; g_sp_capr1 = reached1;
   return DESCO_OK;
 }
 

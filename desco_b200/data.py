@@ -251,7 +251,7 @@ def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: in
         max_rows=max_nv,  # rows of the largest neighborhood (selects the fused SHMP kernel)
     )
     if large:
-        batch._cache["tier"] = lwork[:C].clone()  # which tier served each centre (0 shared, 1 global hash, 2 dense)
+        batch._cache["tier"] = lwork[:C].clone()  # which tier served each centre (0 shared-memory hash, 1 team bitmap)
     return batch
 
 

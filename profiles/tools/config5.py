@@ -78,7 +78,7 @@ def main():
     mine = starts[rank::world]
     part_ms = shmp_ms = types_ms = 0.0
     G = V = E = X = P = 0
-    tiers = np.zeros(3, dtype=np.int64)
+    tiers = np.zeros(2, dtype=np.int64)
     max_rows = 0
     warm = torch.arange(0, min(args.chunk, 256), dtype=torch.int32, device=dev)
     b = partition_batch(g, warm, args.depth, "hetero")
@@ -111,7 +111,7 @@ def main():
         E += batch.num_edges
         max_rows = max(max_rows, batch.max_rows)
         if "tier" in batch._cache:
-            tiers += np.bincount(batch._cache["tier"].cpu().numpy(), minlength=3)[:3]
+            tiers += np.bincount(batch._cache["tier"].cpu().numpy(), minlength=2)[:2]
         # reference-formulation traffic of the k-hop BFS at depth 2: P = nodes expanded (distance <= 1),
         # X = adjacency entries of those nodes
         cl = centres.long()
@@ -156,7 +156,7 @@ def main():
             "workload": f"powerlaw_chunglu_{N}nodes_{M // 2}undirected_edges", "n_gpus": world, "depth": args.depth,
             "partition": {
                 "centres": args.chunk * args.chunks * world, "neighborhoods": G, "rows": V, "directed_edges": E,
-                "max_rows": max_rows, "tier_counts_shared_globalhash_dense": tiers,
+                "max_rows": max_rows, "tier_counts_sharedhash_teambitmap": tiers,
                 "ms": part_ms, "of_which_shmp_typing_ms": types_ms, "centres_per_s": args.chunk * args.chunks * world / (part_ms * 1e-3),
                 "neighborhoods_per_s": G / (part_ms * 1e-3),
                 "algorithmic_bytes": part_bytes, "achieved_gbs": part_bytes / (part_ms * 1e-3) / 1e9,

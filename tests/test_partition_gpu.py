@@ -140,7 +140,7 @@ def test_drop_in_single_centre_api(cuda_device):
 
 
 # ---------------------------------------------------------------------------------------------
-# large-graph regime (config 5): sparse hash-set tiers + dense global-bitset tier
+# large-graph regime (config 5): shared-memory hash-set tier + cooperative team tier (global bitmaps)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["kat", "mutag24", "enzymes12", "imdb6"])
 @pytest.mark.parametrize("mode", ["hetero", "canonical"])
@@ -155,8 +155,8 @@ def test_large_path_matches_reference_golden(cuda_device, golden_dir, name, mode
 
 @pytest.mark.parametrize("caps,label", [
     (DEFAULT_CAPS, "tier0"),
-    ((9, 16, 8, 12, 512, 256), "tier0+1"),        # tier 0 holds 16 members / 8 rows: most centres spill to tier 1
-    ((9, 16, 8, 9, 24, 16), "tier0+1+dense"),     # tier 1 is tiny too: the larger balls reach the dense bitset tier
+    ((9, 16, 8, 12, 512, 256), "tier0+team"),     # tier 0 holds 16 members / 8 rows: most centres go to the team tier
+    ((9, 1, 1, 9, 24, 16), "team-only"),          # tier 0 holds one member: every centre with a neighbour is a team job
 ])
 def test_large_path_every_tier_matches_oracle(cuda_device, large_caps, caps, label):
     from oracle import partition as P
