@@ -93,6 +93,7 @@ SIGNATURES = {
     "desco_partition_large_count": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
     "desco_partition_large_fill": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
     "desco_partition_large_set_caps": (_I, [_I, _I, _I, _I, _I, _I]),
+    "desco_partition_large_phase_cycles": (_I, [_VP, _I]),
     "desco_shmp_edge_types": (_I, [_VP, _VP, _I, _VP, _VP]),
     "desco_shmp_workspace_bytes": (_L, [_I, _I, _I]),
     "desco_shmp_layer_weight_floats": (_L, []),

@@ -620,7 +620,7 @@ __global__ void edge_types_kernel(const int32_t* __restrict__ edge_ptr, const in
 //   * an open-addressing hash set of node ids (linear probing, atomicCAS insert; bit 31 of a key = "reached" flag),
 //   * the member list L in discovery order (BFS levels are contiguous slices of it),
 //   * the reached list R (component of the centre), bitonic-sorted at the end so that rows come out in ascending node
-//     id and a local id is a binary search.
+//     id; the local id of a node is then parked beside its hash slot (uint16 table aliasing the dead member list).
 // A centre whose ball overflows these tables is appended to the big-centre list and served by the team tier below.
 // The sorted adjacency makes "<= centre" a PREFIX of every row, so the restricted passes stop at the first neighbour
 // above the centre.
@@ -675,15 +675,11 @@ struct SparseSet {
     const int s = find(v);
     return s >= 0 && (keys[s] & SP_FLAG);
   }
-  __device__ __forceinline__ int local_id(int v, int n) const {  // index of v in the sorted R[0,n)
-    int a = 0, b = n;
-    while (a < b) {
-      const int m = (a + b) >> 1;
-      if ((int)R[m] < v) a = m + 1; else b = m;
-    }
-    return a;
-  }
 };
+
+// phase timing of the shared-memory tier (thread 0 of every CTA adds its clock64 deltas; desco_partition_large_phase_cycles)
+enum { SPH_EXPAND = 0, SPH_COMPONENT, SPH_SORT, SPH_DEGREE, SPH_EMIT, SPH_WIPE, SPH_COUNT };
+__device__ unsigned long long g_sparse_phase_cycles[SPH_COUNT];
 
 __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const SparseArgs p) {
   extern __shared__ uint32_t sp_smem[];
@@ -692,7 +688,9 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
   set.log2H = p.log2H; set.H = 1 << p.log2H; set.capL = p.capL; set.capR = p.capR;
   set.keys = sp_smem;
   set.L = set.keys + set.H;
-  set.R = set.L + p.capL;
+  set.R = set.L + max(p.capL, set.H / 2);
+  // local id of the node in hash slot s, written after the sort; aliases the member list (dead by then)
+  uint16_t* rank16 = reinterpret_cast<uint16_t*>(set.L);
   set.nL = &s_nL; set.nR = &s_nR; set.over = &s_over;
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   constexpr int NW = SP_THREADS / 32;
@@ -723,6 +721,14 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
     if (tid == 0) set.insert(centre);
     __syncthreads();
 
+    long long tick = clock64();
+    auto lap = [&](int phase) {
+      if (tid == 0) {
+        const long long now = clock64();
+        atomicAdd(&g_sparse_phase_cycles[phase], (unsigned long long)(now - tick));
+        tick = now;
+      }
+    };
     // ---- phase A: k levels of frontier expansion (data.py:329-350); one warp per frontier node ----
     int lb = 0, le = 1;
     bool over = false;
@@ -746,6 +752,7 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
       __syncthreads();
     }
 
+    lap(SPH_EXPAND);
     // ---- phase B + C: candidates <= centre (data.py:385), component of the centre inside them (:387-390) ----
     if (!over) {
       if (p.mode == DESCO_MODE_HETERO) {
@@ -761,20 +768,29 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
           for (int i = qb + warp; i < qe; i += NW) {
             const int u = (int)set.R[i];
             const int rb = rowptr[u], re = rowptr[u + 1];
+            int cnt = 0;  // every member <= centre next to a reached node is reached too: this IS the induced degree
             for (int e0 = rb; e0 < re; e0 += 32) {
               const int e = e0 + lane;
               const int v = (e < re) ? col[e] : 0x7fffffff;
               if (e < re && v <= centre) {
                 const int s = set.find(v);
-                if (s >= 0 && !(set.keys[s] & SP_FLAG)) {
-                  const uint32_t old = atomicOr(&set.keys[s], SP_FLAG);
-                  if (!(old & SP_FLAG)) {
-                    const int idx = atomicAdd(&s_nR, 1);
-                    if (idx < set.capR) set.R[idx] = (uint32_t)v; else s_over = 1;
+                if (s >= 0) {
+                  ++cnt;
+                  if (!(set.keys[s] & SP_FLAG)) {
+                    const uint32_t old = atomicOr(&set.keys[s], SP_FLAG);
+                    if (!(old & SP_FLAG)) {
+                      const int idx = atomicAdd(&s_nR, 1);
+                      if (idx < set.capR) set.R[idx] = (uint32_t)v; else s_over = 1;
+                    }
                   }
                 }
               }
               if (__any_sync(FULL_MASK, e < re && v > centre)) break;
+            }
+            cnt = warp_sum(cnt);
+            if (lane == 0) {
+              rank16[set.find(u)] = (uint16_t)min(cnt, 0xffff);  // parked beside the hash slot until the sort
+              atomicAdd(&s_cnt, cnt);
             }
           }
           __syncthreads();
@@ -815,6 +831,7 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
       continue;
     }
 
+    lap(SPH_COMPONENT);
     // ---- phase D: sort the reached list -> ascending node ids (canonical node = last row) ----
     const int nv = s_nR;
     int n2 = 1;
@@ -838,9 +855,18 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
       }
     }
 
+    lap(SPH_SORT);
     // ---- induced degrees (count pass: just the total) ----
     const int n0 = p.fill ? p.node_off[ci] : 0;
     const int eo = p.fill ? p.edge_off[ci] : 0;
+    if (p.mode == DESCO_MODE_HETERO) {  // degrees were counted by the component BFS
+      if (p.fill)
+        for (int i = tid; i < nv; i += SP_THREADS) {
+          const int u = (int)set.R[i];
+          p.node_gid[n0 + i] = u;
+          p.edge_ptr[n0 + 1 + i] = (int)rank16[set.find(u)];
+        }
+    } else
     for (int i = warp; i < nv; i += NW) {
       const int u = (int)set.R[i];
       const int rb = rowptr[u], re = rowptr[u + 1];
@@ -862,6 +888,7 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
       }
     }
     __syncthreads();
+    lap(SPH_DEGREE);
     if (!p.fill) {
       if (tid == 0) {
         const int ne = s_cnt;
@@ -883,6 +910,8 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
       }
       __syncthreads();
       // edges in adjacency order (ascending node id == ascending local id); types follow in edge_types_kernel
+      for (int i = tid; i < nv; i += SP_THREADS) rank16[set.find((int)set.R[i])] = (uint16_t)i;
+      __syncthreads();
       for (int i = warp; i < nv; i += NW) {
         const int u = (int)set.R[i];
         const int rb = rowptr[u], re = rowptr[u + 1];
@@ -890,19 +919,22 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
         for (int e0 = rb; e0 < re; e0 += 32) {
           const int e = e0 + lane;
           const int v = (e < re) ? col[e] : 0x7fffffff;
-          const bool ok = e < re && v <= limit && set.reached(v);
+          const int slot = (e < re && v <= limit) ? set.find(v) : -1;
+          const bool ok = slot >= 0 && (set.keys[slot] & SP_FLAG);
           const uint32_t m = __ballot_sync(FULL_MASK, ok);
-          if (ok) p.edge_col[out + __popc(m & ((1u << lane) - 1u))] = n0 + set.local_id(v, nv);
+          if (ok) p.edge_col[out + __popc(m & ((1u << lane) - 1u))] = n0 + (int)rank16[slot];
           out += __popc(m);
           if (__any_sync(FULL_MASK, e < re && v > limit)) break;
         }
       }
     }
     __syncthreads();
+    lap(SPH_EMIT);
 
     // ---- wipe the table ----
     for (int i = tid; i < set.H; i += SP_THREADS) set.keys[i] = SP_EMPTY;
     __syncthreads();
+    lap(SPH_WIPE);
   }
 }
 
@@ -1337,7 +1369,8 @@ int launch_partition_large(const int32_t* rowptr, const int32_t* col, const int3
     DESCO_CUDA_TRY(cudaMemsetAsync(base + l.slices_off + (size_t)t * l.slice_bytes, 0, (size_t)l.max_words * 12, stream));
   {  // tier 0: shared memory
     a.tier = 0; a.log2H = g_sp_log2h0; a.capL = g_sp_capl0; a.capR = g_sp_capr0;
-    const size_t smem = (((size_t)1 << a.log2H) + a.capL + a.capR) * 4;
+    const size_t hslots = (size_t)1 << a.log2H;
+    const size_t smem = (hslots + (hslots / 2 > (size_t)a.capL ? hslots / 2 : (size_t)a.capL) + a.capR) * 4;
     if (smem > 200 * 1024) return DESCO_EINVAL;
     DESCO_CUDA_TRY(cudaFuncSetAttribute(partition_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -1516,7 +1549,8 @@ int desco_partition_large_set_caps(int32_t log2_slots0, int32_t members0, int32_
                                    int32_t members1, int32_t reached1) {
   auto pow2 = [](int x) { return x > 0 && (x & (x - 1)) == 0; };
   (void)log2_slots1; (void)members1; (void)reached1;  // the team tier has no capacity limit (bitmaps over the target graph)
-  if (log2_slots0 < 4 || log2_slots0 > 15 || !pow2(reached0) || members0 < 1 || members0 + SP_THREADS > (1 << log2_slots0))
+  if (log2_slots0 < 4 || log2_slots0 > 15 || !pow2(reached0) || reached0 > 32768 || members0 < 1 ||
+      members0 + SP_THREADS > (1 << log2_slots0))
     return DESCO_EINVAL;
   g_sp_log2h0 = log2_slots0; g_sp_capl0 = members0; g_sp_capr0 = reached0;
   return DESCO_OK;
@@ -1544,6 +1578,18 @@ int desco_partition_large_fill(const int32_t* rowptr, const int32_t* col, const 
                                         edge_col, edge_tri, status, workspace, workspace_bytes, (cudaStream_t)stream);
   if (rc) return rc;
   return desco_shmp_edge_types(edge_ptr, edge_col, num_rows, edge_tri, stream);  // SHMP types of the whole packed batch
+}
+
+int desco_partition_large_phase_cycles(uint64_t* out, int32_t reset) {
+  if (!out) return DESCO_EINVAL;
+  unsigned long long h[SPH_COUNT];
+  DESCO_CUDA_TRY(cudaMemcpyFromSymbol(h, g_sparse_phase_cycles, sizeof(h)));
+  for (int i = 0; i < SPH_COUNT; ++i) out[i] = h[i];
+  if (reset) {
+    for (int i = 0; i < SPH_COUNT; ++i) h[i] = 0;
+    DESCO_CUDA_TRY(cudaMemcpyToSymbol(g_sparse_phase_cycles, h, sizeof(h)));
+  }
+  return DESCO_OK;
 }
 
 const char* desco_version(void) { return "desco_b200 0.1 sm_100a"; }

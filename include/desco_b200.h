@@ -109,6 +109,9 @@ int desco_partition_large_fill(const int32_t* rowptr, const int32_t* col, const 
  * Defaults 13/5120/4096 and 19/262144/262144; the tests shrink them to force every tier on small graphs. */
 int desco_partition_large_set_caps(int32_t log2_slots0, int32_t members0, int32_t reached0, int32_t log2_slots1,
                                    int32_t members1, int32_t reached1);
+/* Profiling aid: clock64 cycles thread 0 of every shared-memory-tier CTA spent per phase since the last reset
+ * (out[6]: frontier expansion, component, sort, induced degrees, edge emission, table wipe). */
+int desco_partition_large_phase_cycles(uint64_t* out, int32_t reset);
 
 /* SHMP typing of an already-built batch / query set (ToTconvHetero applied to existing graphs, transforms.py:180-255;
  * also used for the query graphs, lightning_model.py:84-85).  Rows must have ascending edge_col. */

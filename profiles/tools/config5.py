@@ -121,6 +121,12 @@ def main():
                                                          - torch.repeat_interleave(torch.cumsum(hi - lo, 0) - (hi - lo), hi - lo))
         X += int(deg[cl].sum() + deg[g.col[idx].long()].sum())
     barrier()
+    import ctypes
+    from desco_b200 import _lib
+    ph = (ctypes.c_uint64 * 6)()
+    _lib.load().desco_partition_large_phase_cycles(ph, 1)
+    ph_tot = float(sum(ph)) or 1.0
+    phases = {k: round(ph[i] / ph_tot, 4) for i, k in enumerate(("expand", "component", "sort", "degree", "emit", "wipe"))}
     part_ms, shmp_ms, types_ms = tmax(part_ms), tmax(shmp_ms), tmax(types_ms)
     G, V, E, X, P = (tsum(v) for v in (G, V, E, X, P))
     tiers = [tsum(t) for t in tiers]
@@ -156,7 +162,7 @@ def main():
             "workload": f"powerlaw_chunglu_{N}nodes_{M // 2}undirected_edges", "n_gpus": world, "depth": args.depth,
             "partition": {
                 "centres": args.chunk * args.chunks * world, "neighborhoods": G, "rows": V, "directed_edges": E,
-                "max_rows": max_rows, "tier_counts_sharedhash_teambitmap": tiers,
+                "max_rows": max_rows, "tier_counts_sharedhash_teambitmap": tiers, "sharedhash_tier_phase_share": phases,
                 "ms": part_ms, "of_which_shmp_typing_ms": types_ms, "centres_per_s": args.chunk * args.chunks * world / (part_ms * 1e-3),
                 "neighborhoods_per_s": G / (part_ms * 1e-3),
                 "algorithmic_bytes": part_bytes, "achieved_gbs": part_bytes / (part_ms * 1e-3) / 1e9,
