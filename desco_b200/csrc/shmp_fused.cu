@@ -36,14 +36,17 @@ constexpr int LDP = 2 * F + 4;          // row pitch (floats) of the P_tri|P_tri
 constexpr int LDS_ = F + 4;             // row pitch (floats) of the fp32 staging rows (P_self, then h')
 constexpr int EDGE_CAP = 8192;          // staged edges per tile (1 byte each); larger tiles read edges from global
 constexpr int CH = SHMP_PLAN_CHUNK;     // neighborhoods per planning chunk
+constexpr int CINP = NB + 8;            // row pitch (bf16) of the canonical-input rows: fragment loads of 8 rows hit 32 banks
 
 // per-layer weight blob (bytes)
 constexpr int OFF_BHI = 0;
 constexpr int OFF_BLO = NB * 128;
 constexpr int OFF_BIASC = 2 * NB * 128;
 constexpr int OFF_BIASA = OFF_BIASC + F * 4;
-constexpr int OFF_WAT = OFF_BIASA + F * 4;        // [64 n][192 k] fp32
-constexpr int OFF_CWT = OFF_WAT + F * NB * 4;     // [128 n][64 k] fp32
+// canonical-row weights as ready-made mma.sync B fragments (tcpack.pack_mma_b_frags): per (column tile of 8, k-step of
+// 16, lane) one uint4 {hi(k..k+1), hi(k+8..k+9), lo(k..k+1), lo(k+8..k+9)} of column 8 nt + lane/4, k = 16 ks + 2 (lane%4)
+constexpr int OFF_WAT = OFF_BIASA + F * 4;        // Wa  [192 k][64 n]  -> [8 nt][12 ks][32 lanes] uint4
+constexpr int OFF_CWT = OFF_WAT + F * NB * 4;     // Cw  [64 k][128 n]  -> [16 nt][4 ks][32 lanes] uint4
 constexpr int LAYER_BYTES = OFF_CWT + 2 * F * F * 4;
 static_assert(LAYER_BYTES == SHMP_TC_LAYER_BYTES, "blob layout and header constant disagree");
 
@@ -54,8 +57,8 @@ constexpr int SM_AHI = SM_BLO + NB * 128;
 constexpr int SM_ALO = SM_AHI + TR * 128;
 constexpr int SM_P = SM_ALO + TR * 128;
 constexpr int SM_STAGE = SM_P + TR * LDP * 4;
-constexpr int SM_CIN = SM_STAGE + TR * LDS_ * 4;        // [MAXC][192]: sum_tri h_j | sum_tride h_j | h_a
-constexpr int SM_CVEC = SM_CIN + MAXC * NB * 4;         // [MAXC][128]
+constexpr int SM_CIN = SM_STAGE + TR * LDS_ * 4;        // bf16 hi then lo, each [MAXC][CINP]: sum_tri h_j | sum_tride h_j | h_a
+constexpr int SM_CVEC = SM_CIN + 2 * MAXC * CINP * 2;   // [MAXC][128]
 constexpr int SM_CH = SM_CVEC + MAXC * 2 * F * 4;       // [MAXC][64]  h_a of the next layer
 constexpr int SM_EDGE = SM_CH + MAXC * F * 4;           // [EDGE_CAP] local col | tri << 7
 constexpr int SM_EPTR = SM_EDGE + EDGE_CAP;             // [TR + 1] int
@@ -66,6 +69,7 @@ constexpr int SM_QUIRK = SM_NBHLO + ((MAXC + 1) * 4 + 15) / 16 * 16;  // [MAXC] 
 constexpr int SM_BARS = SM_QUIRK + (MAXC * 4 + 15) / 16 * 16;         // 2 mbarriers + tmem slot
 constexpr int SM_TOTAL = SM_BARS + 64;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;  // slack for the manual 1024-B alignment
+static_assert(MAXC <= 32 && MAXC * CINP * 2 + MAXC * 3 * F * 4 >= 32 * CINP * 2, "the second mma row block reads (and ignores) rows past MAXC");
 static_assert(SMEM_BYTES <= 232448, "fused SHMP kernel exceeds the 227 KB shared-memory limit");
 static_assert(SM_AHI % 1024 == 0 && SM_ALO % 1024 == 0 && SM_BLO % 1024 == 0, "UMMA tiles must be 1024-B aligned");
 
@@ -75,7 +79,8 @@ static_assert(SM_AHI % 1024 == 0 && SM_ALO % 1024 == 0 && SM_BLO % 1024 == 0, "U
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) shmp_tile_plan_kernel(const int32_t* __restrict__ nbh_ptr, int G,
                                                               int32_t* __restrict__ tile_start,
-                                                              int32_t* __restrict__ tile_count, int32_t* __restrict__ status) {
+                                                              int32_t* __restrict__ tile_count, int32_t* __restrict__ ticket,
+                                                              int32_t* __restrict__ status) {
   __shared__ int sP[CH + 1], sJa[CH + 1], sJb[CH + 1], sS[CH + 1];
   __shared__ int s_cnt;
   const int tid = threadIdx.x;
@@ -119,6 +124,7 @@ __global__ void __launch_bounds__(1024) shmp_tile_plan_kernel(const int32_t* __r
   int32_t* out = tile_start + (size_t)blockIdx.x * (CH + 1);
   for (int t = tid; t <= count; t += 1024) out[t] = c0 + sS[t];
   if (tid == 0) tile_count[blockIdx.x] = count;
+  if (tid == 0 && blockIdx.x == 0) *ticket = 0;  // the fused kernel deals tiles through this counter
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -130,7 +136,7 @@ __device__ unsigned long long g_phase_cycles[PH_COUNT];
 
 struct FusedArgs {
   const int32_t* nbh_ptr; const int32_t* edge_ptr; const int32_t* edge_col; const uint8_t* edge_tri;
-  const int32_t* tile_start; const int32_t* tile_count;
+  const int32_t* tile_start; const int32_t* tile_count; int32_t* ticket;
   int G, num_chunks, pyg_batch_size, layers, passes, input_dim, emb_ld;
   const float* feat;        // [V][input_dim] or NULL (ZeroNodeFeat)
   const float* w_pre;       // per node type (count, canonical): W[input_dim][64], b[64]
@@ -140,7 +146,12 @@ struct FusedArgs {
   int32_t* status;
 };
 
-__device__ __forceinline__ void add2(float2& a, const float2 b) { a.x += b.x; a.y += b.y; }
+// D(16x8, fp32) += A(16x16, bf16, row) . B(16x8, bf16, col) on the warp-level tensor path
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs p) {
@@ -153,7 +164,8 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
   uint8_t* sAlo = smem + SM_ALO;
   float* sP = reinterpret_cast<float*>(smem + SM_P);
   float* sStage = reinterpret_cast<float*>(smem + SM_STAGE);
-  float* sCin = reinterpret_cast<float*>(smem + SM_CIN);
+  __nv_bfloat16* sCinHi = reinterpret_cast<__nv_bfloat16*>(smem + SM_CIN);
+  __nv_bfloat16* sCinLo = sCinHi + MAXC * CINP;
   float* sCvec = reinterpret_cast<float*>(smem + SM_CVEC);
   float* sCh = reinterpret_cast<float*>(smem + SM_CH);
   uint8_t* sEdge = smem + SM_EDGE;
@@ -167,18 +179,15 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // how many tiles does this CTA own?  (tiles are dealt round-robin over the flattened (chunk, tile) list)
-  int my_tiles = 0;
-  {
-    int base = 0;
-    for (int c = 0; c < p.num_chunks; ++c) {
-      const int cnt = p.tile_count[c];
-      const int first = (int)((blockIdx.x + gridDim.x - (base % gridDim.x)) % gridDim.x);
-      if (first < cnt) my_tiles += (cnt - first + gridDim.x - 1) / gridDim.x;
-      base += cnt;
-    }
-  }
-  if (my_tiles == 0) return;
+  // tiles are dealt dynamically (one atomic ticket per tile over the flattened (chunk, tile) list): tile costs vary by
+  // ~2x with the number of neighborhoods / edges in the tile, and a static round-robin left the slowest CTA 1.5x behind
+  __shared__ int s_ticket;
+  int total_tiles = 0;
+  for (int c = 0; c < p.num_chunks; ++c) total_tiles += p.tile_count[c];
+  if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
+  __syncthreads();
+  int cur_tile = s_ticket;
+  if (cur_tile >= total_tiles) return;
 
   if (tid == 0) {
     tc05::mbar_init(&bars[0], 1);
@@ -197,19 +206,18 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
   }
   bool copy_pending = true;  // meaningful in the ISSUER thread only
   uint32_t wphase = 0, mphase = 0;
-  int tiles_done = 0;
   bool timed_out = false;
   const uint32_t idesc = tc05::make_idesc_bf16(TR, NB);
   const int hw = lane >> 4, hl = lane & 15;  // half-warp id / lane inside the half-warp (one half-warp per row)
 
-  int chunk_base = 0;
-  for (int c = 0; c < p.num_chunks; ++c) {
-    const int cnt = p.tile_count[c];
-    const int first = (int)((blockIdx.x + gridDim.x - (chunk_base % gridDim.x)) % gridDim.x);
-    chunk_base += cnt;
-    for (int t = first; t < cnt; t += gridDim.x) {
+  while (cur_tile < total_tiles) {
+    {
+      int c = 0, t = cur_tile;
+      while (t >= p.tile_count[c]) t -= p.tile_count[c++];
       const int32_t* ts = p.tile_start + (size_t)c * (CH + 1);
       const int nb0 = ts[t], nb1 = ts[t + 1];
+      __syncthreads();  // previous tile fully retired (s_ticket included)
+      if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);  // the ticket of the NEXT tile: known before the last layer's prefetch
       const int nc = nb1 - nb0;                    // neighborhoods in the tile
       const int row0 = p.nbh_ptr[nb0];
       const int R = p.nbh_ptr[nb1] - row0;         // rows in the tile
@@ -217,7 +225,8 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
       const int Et = p.edge_ptr[row0 + R] - e0;
       const bool edges_staged = Et <= EDGE_CAP;
       if (R > TR || nc > MAXC) {  // the plan kernel has already raised DESCO_ERANGE; never overrun the tile buffers
-        ++tiles_done;
+        __syncthreads();
+        cur_tile = s_ticket;
         continue;
       }
 
@@ -230,7 +239,6 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
           tick = now;
         }
       };
-      __syncthreads();  // previous tile fully retired
       if (tid <= nc) sNbhLo[tid] = p.nbh_ptr[nb0 + tid] - row0;
       if (tid < nc) {
         // SAGEConv.forward runs remove_self_loops on the bipartite count<->canonical relations (gnn_model.py:389-390):
@@ -328,19 +336,22 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
           tc05::mma_commit(&bars[1]);
         }
         if (l < p.layers) wphase ^= 1;
-        // this thread's slice of the canonical-row weights of layer l: issued now, consumed after the pool phase
+        // this warp's B fragments of the canonical-row weights of layer l: issued now, consumed after the pool phase.
+        // Warps 0-7: z_a column tile `warp` (K = 192, 12 k-steps); warps 8-15: cvec column tiles 2(warp-8), 2(warp-8)+1
+        // (K = 64, 4 k-steps each).
         const uint8_t* wl = p.w_layers + (size_t)(l < p.layers ? l : 0) * LAYER_BYTES;
-        const int kq = tid & 7, kh = tid & 3;
-        float4 wa[NB / 32], wc[F / 16];
-        float bias_an = 0.f;
+        const int fg = lane >> 2, ft = lane & 3;  // mma fragment coordinates: group (row / column), thread in group
+        uint4 wf[12];
         if (l < p.layers) {
-          const float* WaT = reinterpret_cast<const float*>(wl + OFF_WAT) + (size_t)(tid >> 3) * NB + 4 * kq;
-          const float* CwT = reinterpret_cast<const float*>(wl + OFF_CWT) + (size_t)(tid >> 2) * F + 4 * kh;
+          if (warp < 8) {
+            const uint4* W = reinterpret_cast<const uint4*>(wl + OFF_WAT) + (size_t)warp * 12 * 32 + lane;
 #pragma unroll
-          for (int kk = 0; kk < NB / 32; ++kk) wa[kk] = __ldg(reinterpret_cast<const float4*>(WaT + 32 * kk));
+            for (int ks = 0; ks < 12; ++ks) wf[ks] = __ldg(W + 32 * ks);
+          } else {
+            const uint4* W = reinterpret_cast<const uint4*>(wl + OFF_CWT) + (size_t)(2 * (warp - 8)) * 4 * 32 + lane;
 #pragma unroll
-          for (int kk = 0; kk < F / 16; ++kk) wc[kk] = __ldg(reinterpret_cast<const float4*>(CwT + 16 * kk));
-          bias_an = __ldg(reinterpret_cast<const float*>(wl + OFF_BIASA) + (tid >> 3));
+            for (int ks = 0; ks < 8; ++ks) wf[ks] = __ldg(W + 32 * ks);
+          }
         }
         // ------------ pool + canonical inputs of layer l (from the fp32 rows of h^l in sStage, h_a^l in sCh) ------------
         // thread = (neighborhood, feature): 64 consecutive features per neighborhood, 8 neighborhoods at a time
@@ -370,9 +381,9 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
                 const float v = (j == quirk) ? 0.f : sStage[j * LDS_ + f];
                 if (b & 0x80) vt += v; else vd += v;
               }
-              sCin[i * NB + f] = vt;
-              sCin[i * NB + F + f] = vd;
-              sCin[i * NB + 2 * F + f] = ha;
+              tc05::split_bf16(vt, sCinHi[i * CINP + f], sCinLo[i * CINP + f]);
+              tc05::split_bf16(vd, sCinHi[i * CINP + F + f], sCinLo[i * CINP + F + f]);
+              tc05::split_bf16(ha, sCinHi[i * CINP + 2 * F + f], sCinLo[i * CINP + 2 * F + f]);
             }
           }
         }
@@ -380,46 +391,52 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         __syncthreads();
         lap(PH_POOL);
 
-        // ------------ canonical rows in fp32 on the CUDA cores (weights in registers), two neighborhoods per trip ------------
-        {
-          const int n = tid >> 3;   // z_a = [sum_tri | sum_tride | h_a] . Wa : thread = (n, kq), k = 32 kk + 4 kq + {0..3}
-          const int n2 = tid >> 2;  // cvec = h_a . [Cw_tri | Cw_tride]       : thread = (n2, kh), k = 16 kk + 4 kh + {0..3}
-          for (int r = 0; r < nc; r += 2) {
-            const bool two = r + 1 < nc;
-            const float* x0 = sCin + r * NB;
-            const float* x1 = sCin + (two ? r + 1 : r) * NB;
-            float va0 = 0.f, va1 = 0.f, vc0 = 0.f, vc1 = 0.f;
+        // ------------ canonical rows on the warp-level tensor path (mma.sync m16n8k16, bf16 hi/lo split, 3 passes:
+        // same fp32-grade products as the tile GEMM); 16 canonical rows per row block ------------
+        for (int mb = 0; mb < nc; mb += 16) {
+          // A fragment registers: rows fg / fg + 8 of the block, bf16 pairs at k = 16 ks + 2 ft (+ 8)
+          const uint32_t* xh0 = reinterpret_cast<const uint32_t*>(sCinHi + (mb + fg) * CINP + 2 * ft);
+          const uint32_t* xl0 = reinterpret_cast<const uint32_t*>(sCinLo + (mb + fg) * CINP + 2 * ft);
+          constexpr int R8 = 8 * CINP / 2, K8 = 4;  // +8 rows / +8 columns in 32-bit words
+          if (warp < 8) {  // z_a = [sum_tri | sum_tride | h_a] . Wa, columns 8 warp .. 8 warp + 7
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-            for (int kk = 0; kk < NB / 32; ++kk) {
-              const float4 a0 = *reinterpret_cast<const float4*>(x0 + 32 * kk + 4 * kq);
-              const float4 a1 = *reinterpret_cast<const float4*>(x1 + 32 * kk + 4 * kq);
-              va0 = fmaf(a0.x, wa[kk].x, fmaf(a0.y, wa[kk].y, fmaf(a0.z, wa[kk].z, fmaf(a0.w, wa[kk].w, va0))));
-              va1 = fmaf(a1.x, wa[kk].x, fmaf(a1.y, wa[kk].y, fmaf(a1.z, wa[kk].z, fmaf(a1.w, wa[kk].w, va1))));
+            for (int ks = 0; ks < 12; ++ks) {
+              const uint32_t ahi[4] = {xh0[8 * ks], xh0[8 * ks + R8], xh0[8 * ks + K8], xh0[8 * ks + R8 + K8]};
+              const uint32_t alo[4] = {xl0[8 * ks], xl0[8 * ks + R8], xl0[8 * ks + K8], xl0[8 * ks + R8 + K8]};
+              mma16816(acc[ks & 1], ahi, wf[ks].x, wf[ks].y);
+              mma16816(acc[ks & 1], alo, wf[ks].x, wf[ks].y);
+              mma16816(acc[ks & 1], ahi, wf[ks].z, wf[ks].w);
             }
+            const int n = 8 * warp + 2 * ft;
+            const float2 b = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(wl + OFF_BIASA) + n));
+            const int r0 = mb + fg, r1 = r0 + 8;  // h_a^{l+1}; read again only after the next barriers
+            if (r0 < nc)
+              *reinterpret_cast<float2*>(sCh + r0 * F + n) =
+                  make_float2(fmaxf(acc[0][0] + acc[1][0] + b.x, 0.f), fmaxf(acc[0][1] + acc[1][1] + b.y, 0.f));
+            if (r1 < nc)
+              *reinterpret_cast<float2*>(sCh + r1 * F + n) =
+                  make_float2(fmaxf(acc[0][2] + acc[1][2] + b.x, 0.f), fmaxf(acc[0][3] + acc[1][3] + b.y, 0.f));
+          } else {  // cvec = h_a . [Cw_tri | Cw_tride], column tiles 2(warp-8), 2(warp-8)+1
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-            for (int kk = 0; kk < F / 16; ++kk) {
-              const float4 a0 = *reinterpret_cast<const float4*>(x0 + 2 * F + 16 * kk + 4 * kh);
-              const float4 a1 = *reinterpret_cast<const float4*>(x1 + 2 * F + 16 * kk + 4 * kh);
-              vc0 = fmaf(a0.x, wc[kk].x, fmaf(a0.y, wc[kk].y, fmaf(a0.z, wc[kk].z, fmaf(a0.w, wc[kk].w, vc0))));
-              vc1 = fmaf(a1.x, wc[kk].x, fmaf(a1.y, wc[kk].y, fmaf(a1.z, wc[kk].z, fmaf(a1.w, wc[kk].w, vc1))));
+            for (int ks = 0; ks < 4; ++ks) {
+              const int w0 = F + 8 * ks;  // the h_a block starts at bf16 column 2F = word F
+              const uint32_t ahi[4] = {xh0[w0], xh0[w0 + R8], xh0[w0 + K8], xh0[w0 + R8 + K8]};
+              const uint32_t alo[4] = {xl0[w0], xl0[w0 + R8], xl0[w0 + K8], xl0[w0 + R8 + K8]};
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                mma16816(acc[j], ahi, wf[4 * j + ks].x, wf[4 * j + ks].y);
+                mma16816(acc[j], alo, wf[4 * j + ks].x, wf[4 * j + ks].y);
+                mma16816(acc[j], ahi, wf[4 * j + ks].z, wf[4 * j + ks].w);
+              }
             }
-            va0 += __shfl_xor_sync(FULL_MASK, va0, 1);
-            va1 += __shfl_xor_sync(FULL_MASK, va1, 1);
-            vc0 += __shfl_xor_sync(FULL_MASK, vc0, 1);
-            vc1 += __shfl_xor_sync(FULL_MASK, vc1, 1);
-            va0 += __shfl_xor_sync(FULL_MASK, va0, 2);
-            va1 += __shfl_xor_sync(FULL_MASK, va1, 2);
-            vc0 += __shfl_xor_sync(FULL_MASK, vc0, 2);
-            vc1 += __shfl_xor_sync(FULL_MASK, vc1, 2);
-            va0 += __shfl_xor_sync(FULL_MASK, va0, 4);
-            va1 += __shfl_xor_sync(FULL_MASK, va1, 4);
-            if (kq == 0) {  // h_a^{l+1}; read again only after the next barriers
-              sCh[r * F + n] = fmaxf(va0 + bias_an, 0.f);
-              if (two) sCh[(r + 1) * F + n] = fmaxf(va1 + bias_an, 0.f);
-            }
-            if (kh == 0) {
-              sCvec[r * 2 * F + n2] = vc0;
-              if (two) sCvec[(r + 1) * 2 * F + n2] = vc1;
+            const int r0 = mb + fg, r1 = r0 + 8;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int n = 8 * (2 * (warp - 8) + j) + 2 * ft;
+              if (r0 < nc) *reinterpret_cast<float2*>(sCvec + r0 * 2 * F + n) = make_float2(acc[j][0], acc[j][1]);
+              if (r1 < nc) *reinterpret_cast<float2*>(sCvec + r1 * 2 * F + n) = make_float2(acc[j][2], acc[j][3]);
             }
           }
         }
@@ -431,7 +448,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         mphase ^= 1;
         tc05::fence_after_sync();
         if (tid == ISSUER) {  // the B images are free again: stream in the next layer's (or the next tile's layer-0) weights
-          const bool last = (tiles_done + 1 == my_tiles) && (l + 1 == p.layers);
+          const bool last = (s_ticket >= total_tiles) && (l + 1 == p.layers);
           if (!last) {
             const int nl = (l + 1) % p.layers;
             tc05::mbar_arrive_expect_tx(&bars[0], layer_image_bytes);
@@ -506,7 +523,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         lap(PH_GATHER);
       }
       lap(PH_POOL);
-      ++tiles_done;
+      cur_tile = s_ticket;
     }
   }
   if (tid == ISSUER && copy_pending) tc05::mbar_wait(&bars[0], wphase);  // never exit with a bulk copy in flight
@@ -532,7 +549,7 @@ extern "C" int desco_shmp_fused_phase_cycles(uint64_t* out, int32_t reset) {
 
 int64_t desco_internal_shmp_fused_workspace_bytes(int num_neighborhoods) {
   const int chunks = (num_neighborhoods + CH - 1) / CH;
-  return (int64_t)(((size_t)chunks * (CH + 1) * 4 + 255) / 256 * 256 + ((size_t)chunks * 4 + 255) / 256 * 256);
+  return (int64_t)(((size_t)chunks * (CH + 1) * 4 + 255) / 256 * 256 + ((size_t)chunks * 4 + 255) / 256 * 256 + 256);
 }
 
 int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col,
@@ -544,9 +561,10 @@ int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge
   const int chunks = (G + CH - 1) / CH;
   int32_t* tile_start = (int32_t*)workspace;
   int32_t* tile_count = (int32_t*)((char*)workspace + ((size_t)chunks * (CH + 1) * 4 + 255) / 256 * 256);
+  int32_t* ticket = (int32_t*)((char*)tile_count + ((size_t)chunks * 4 + 255) / 256 * 256);
   {
     DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
-    shmp_tile_plan_kernel<<<chunks, 1024, 0, s>>>(nbh_ptr, G, tile_start, tile_count, status);
+    shmp_tile_plan_kernel<<<chunks, 1024, 0, s>>>(nbh_ptr, G, tile_start, tile_count, ticket, status);
     DESCO_LAUNCH_CHECK();
   }
   static bool attr_set = false;
@@ -556,7 +574,7 @@ int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge
   }
   FusedArgs a;
   a.nbh_ptr = nbh_ptr; a.edge_ptr = edge_ptr; a.edge_col = edge_col; a.edge_tri = edge_tri;
-  a.tile_start = tile_start; a.tile_count = tile_count;
+  a.tile_start = tile_start; a.tile_count = tile_count; a.ticket = ticket;
   a.G = G; a.num_chunks = chunks; a.pyg_batch_size = pyg_batch_size; a.layers = layers; a.passes = passes;
   a.input_dim = input_dim; a.emb_ld = emb_ld;
   a.feat = feat; a.w_pre = w_pre; a.w_layers = (const uint8_t*)w_layers_tc; a.emb_a = emb_a; a.pool = pool; a.status = status;

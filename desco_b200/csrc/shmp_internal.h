@@ -8,7 +8,7 @@
 #define SHMP_TILE_MAX_NBH 20   /* neighborhoods per fused tile (bounds the canonical-row buffers)    */
 #define SHMP_PLAN_CHUNK 2048   /* neighborhoods per tile-planning CTA; tiles never straddle chunks   */
 /* bytes of one layer in the tensor-core weight blob: B hi/lo images (2 x 192 x 128), bias_c, bias_a (64 fp32 each),
- * WaT [64][192] fp32, CwT [128][64] fp32 */
+ * Wa [192][64] and Cw [64][128] as mma.sync B fragments (bf16 hi/lo, tcpack.pack_mma_b_frags; same bytes as fp32) */
 #define SHMP_TC_LAYER_BYTES (2 * 192 * 128 + 2 * 64 * 4 + 64 * 192 * 4 + 128 * 64 * 4)
 
 int64_t desco_internal_shmp_fused_workspace_bytes(int num_neighborhoods);

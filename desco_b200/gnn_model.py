@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import _lib
 from .data import NeighborhoodBatch, _ptr, _stream
-from .tcpack import pack_b_operand, pack_dense_tc
+from .tcpack import pack_b_operand, pack_dense_tc, pack_mma_b_frags
 
 TARGET_META = (
     ["count", "canonical"],
@@ -168,7 +168,7 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
         if hetero:  # tensor-core form (csrc/shmp_fused.cu): B operand rows n = output column, k contiguous
             B = torch.cat([Wc[0:F].t(), Wc[F:2 * F].t(), Wc[2 * F:3 * F].t()], 0)  # [192][64]
             f32b = lambda t: t.to(torch.float32).contiguous().view(torch.uint8).reshape(-1)
-            tc_layers += [pack_b_operand(B), f32b(bias_c), f32b(bias_a), f32b(Wa.t()), f32b(Cw.t())]
+            tc_layers += [pack_b_operand(B), f32b(bias_c), f32b(bias_a), pack_mma_b_frags(Wa), pack_mma_b_frags(Cw)]
     ro = [d(base.anchor_mlp[0].weight).t().contiguous().flatten(), d(base.anchor_mlp[0].bias)]
     for i in (0, 3, 5, 7):
         ro += [d(base.post_mp[i].weight).t().contiguous().flatten(), d(base.post_mp[i].bias)]

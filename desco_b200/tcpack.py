@@ -59,3 +59,25 @@ def pack_dense_tc(w: torch.Tensor, nblk: int) -> torch.Tensor:
             blk = w[nb * nblk:(nb + 1) * nblk, a * 64:(a + 1) * 64]
             parts += [swizzle_rows(x) for x in split_bf16_3(blk)]
     return torch.cat(parts)
+
+
+def pack_mma_b_frags(w: torch.Tensor) -> torch.Tensor:
+    """W[K, N] (K-major weight, K % 16 == 0, N % 8 == 0) -> uint8 image of warp-level ``mma.sync.m16n8k16`` B fragments,
+    bf16 hi/lo split: for column tile nt, k-step ks and lane (g = lane // 4, t = lane % 4) one 16-byte record
+    ``{hi[k0:k0+2], hi[k0+8:k0+10], lo[k0:k0+2], lo[k0+8:k0+10]}`` of column ``8 nt + g`` with ``k0 = 16 ks + 2 t``
+    (csrc/shmp_fused.cu: the canonical rows of a tile).  Same byte count as the fp32 matrix."""
+    w = w.detach().cpu()
+    k, n = w.shape
+    assert k % 16 == 0 and n % 8 == 0, (k, n)
+    hi, lo = split_bf16(w)
+    hi, lo = hi.view(torch.int16), lo.view(torch.int16)
+    lane = torch.arange(32)
+    g, t = lane // 4, lane % 4
+    k0 = (16 * torch.arange(k // 16).view(1, -1, 1) + 2 * t.view(1, 1, 32)).expand(n // 8, k // 16, 32)
+    col = (8 * torch.arange(n // 8).view(-1, 1, 1) + g.view(1, 1, 32)).expand(n // 8, k // 16, 32)
+    parts = []
+    for src in (hi, lo):
+        for off in (0, 8):
+            parts += [src[k0 + off, col], src[k0 + off + 1, col]]
+    out = torch.stack(parts, dim=-1)  # [nt, ks, lane, 8 bf16]
+    return out.contiguous().view(torch.uint8).reshape(-1)
