@@ -66,7 +66,8 @@ constexpr int SM_ROWG = SM_EPTR + ((TR + 1) * 4 + 15) / 16 * 16;  // [TR] uint8 
 constexpr int SM_ROWCODE = SM_ROWG + TR;                // [TR] uint8: 0 none, 1 tri / 2 tride edge to canonical, 3 canonical
 constexpr int SM_NBHLO = SM_ROWCODE + TR;               // [MAXC + 1] int local first row
 constexpr int SM_QUIRK = SM_NBHLO + ((MAXC + 1) * 4 + 15) / 16 * 16;  // [MAXC] int local row or -1
-constexpr int SM_BARS = SM_QUIRK + (MAXC * 4 + 15) / 16 * 16;         // 2 mbarriers + tmem slot
+constexpr int SM_BIASC = SM_QUIRK + (MAXC * 4 + 15) / 16 * 16;        // [64] float: bias of the count rows, this layer
+constexpr int SM_BARS = SM_BIASC + F * 4;                             // 2 mbarriers + tmem slot
 constexpr int SM_TOTAL = SM_BARS + 64;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;  // slack for the manual 1024-B alignment
 static_assert(MAXC <= 32 && MAXC * CINP * 2 + MAXC * 3 * F * 4 >= 32 * CINP * 2, "the second mma row block reads (and ignores) rows past MAXC");
@@ -152,7 +153,22 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+// a += b as two packed fp32x2 adds (sm_100 FADD2: half the issue slots of four scalar adds; same rounding)
+__device__ __forceinline__ void add4(float4& a, const float4 b) {
+  asm("{\n\t.reg .b64 ra, rb;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%6, %7};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%2, %3}, ra;\n\t}"
+      : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)
+      : "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w));
+}
+// four fp32 -> bf16 hi / lo pairs with the packed converts (x = hi + lo + O(2^-17 |x|), as tc05::split_bf16)
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
 
 __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -174,6 +190,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
   uint8_t* sRowCode = smem + SM_ROWCODE;
   int* sNbhLo = reinterpret_cast<int*>(smem + SM_NBHLO);
   int* sQuirk = reinterpret_cast<int*>(smem + SM_QUIRK);
+  float* sBiasC = reinterpret_cast<float*>(smem + SM_BIASC);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);  // [0] weights landed, [1] MMA done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
@@ -342,7 +359,11 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         const uint8_t* wl = p.w_layers + (size_t)(l < p.layers ? l : 0) * LAYER_BYTES;
         const int fg = lane >> 2, ft = lane & 3;  // mma fragment coordinates: group (row / column), thread in group
         uint4 wf[12];
+        // biases of this layer, fetched here too so that their L2 latency hides under the pool phase
+        float2 bias_a = make_float2(0.f, 0.f);
         if (l < p.layers) {
+          if (tid < F) sBiasC[tid] = __ldg(reinterpret_cast<const float*>(wl + OFF_BIASC) + tid);  // read after two barriers
+          if (warp < 8) bias_a = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(wl + OFF_BIASA) + 8 * warp + 2 * ft));
           if (warp < 8) {
             const uint4* W = reinterpret_cast<const uint4*>(wl + OFF_WAT) + (size_t)warp * 12 * 32 + lane;
 #pragma unroll
@@ -409,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
               mma16816(acc[ks & 1], ahi, wf[ks].z, wf[ks].w);
             }
             const int n = 8 * warp + 2 * ft;
-            const float2 b = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(wl + OFF_BIASA) + n));
+            const float2 b = bias_a;
             const int r0 = mb + fg, r1 = r0 + 8;  // h_a^{l+1}; read again only after the next barriers
             if (r0 < nc)
               *reinterpret_cast<float2*>(sCh + r0 * F + n) =
@@ -475,47 +496,64 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         __syncthreads();
         lap(PH_T2S);
 
-        // ------------ segmented, edge-type-split gather out of shared memory; one half-warp per row ------------
-        // the edge records of a row are fetched by the lanes of its half-warp in one go and broadcast by shuffle, so
-        // the P-row loads of consecutive edges are independent and overlap
+        // ------------ segmented, edge-type-split gather out of shared memory; one quarter-warp per row ------------
+        // lane q of a quarter owns features 4q..4q+3 and 32+4q..32+4q+3 (two conflict-free 128-byte row halves per
+        // quarter and two independent accumulators per lane); the edge records of a row are fetched eight at a time by
+        // the lanes of its quarter and broadcast by shuffle, so the P-row loads of consecutive edges overlap
         {
-          const float4 bias = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(wl + OFF_BIASC) + 4 * hl);
-          for (int rb = warp * 2; rb < R; rb += 2 * NWARPS) {
-            const int r = rb + hw;
+          const int rw = lane >> 3, q = lane & 7;
+          for (int rb = warp * 4; rb < R; rb += 4 * NWARPS) {
+            const int r = rb + rw;
             const int code = (r < R) ? sRowCode[r] : 3;
-            const bool active = code != 3;  // canonical rows were done on the CUDA cores above
+            const bool active = code != 3;  // canonical rows were done on the warp-level tensor path above
             int eb = 0, ee = 0;
             if (active) { eb = sEptr[r]; ee = sEptr[r + 1]; }
             const int deg = ee - eb;
-            const int nsh = min(deg, 16);
-            const int myb = (hl < nsh) ? edge_at(eb + hl) : 0;
-            const int nmax = max(nsh, __shfl_xor_sync(FULL_MASK, nsh, 16));
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int dmax = max(deg, __shfl_xor_sync(FULL_MASK, deg, 8));
+            dmax = max(dmax, __shfl_xor_sync(FULL_MASK, dmax, 16));  // warp-uniform trip count
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
             if (active) {
-              acc = *reinterpret_cast<const float4*>(sStage + r * LDS_ + 4 * hl);  // P_self
-              add4(acc, bias);
+              const float* self = sStage + r * LDS_ + 4 * q;  // P_self
+              a0 = *reinterpret_cast<const float4*>(self);
+              a1 = *reinterpret_cast<const float4*>(self + 32);
+              add4(a0, *reinterpret_cast<const float4*>(sBiasC + 4 * q));
+              add4(a1, *reinterpret_cast<const float4*>(sBiasC + 32 + 4 * q));
             }
+            for (int c0 = 0; c0 < dmax; c0 += 8) {
+              const int myb = (c0 + q < deg) ? edge_at(eb + c0 + q) : -1;
+              const int cnt = min(8, dmax - c0);
 #pragma unroll 4
-            for (int k = 0; k < nmax; ++k) {
-              const int b = __shfl_sync(FULL_MASK, myb, k, 16);
-              // (an edge to the canonical row adds its P row, which is exactly 0: canonical rows of A are zero and
-              //  the canonical -> count message arrives through cvec instead)
-              if (k < nsh) add4(acc, *reinterpret_cast<const float4*>(sP + (b & 127) * LDP + ((b & 0x80) ? 0 : F) + 4 * hl));
-            }
-            for (int e = eb + 16; e < ee; ++e) {
-              const int b = edge_at(e);
-              add4(acc, *reinterpret_cast<const float4*>(sP + (b & 127) * LDP + ((b & 0x80) ? 0 : F) + 4 * hl));
+              for (int k = 0; k < cnt; ++k) {
+                const int b = __shfl_sync(FULL_MASK, myb, k, 8);
+                // (an edge to the canonical row adds its P row, which is exactly 0: canonical rows of A are zero and
+                //  the canonical -> count message arrives through cvec instead)
+                if (b >= 0) {
+                  const float* src = sP + (b & 127) * LDP + ((b & 0x80) ? 0 : F) + 4 * q;
+                  add4(a0, *reinterpret_cast<const float4*>(src));
+                  add4(a1, *reinterpret_cast<const float4*>(src + 32));
+                }
+              }
             }
             if (!active) continue;
-            if (code) add4(acc, *reinterpret_cast<const float4*>(sCvec + sRowG[r] * 2 * F + (code - 1) * F + 4 * hl));
-            acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-            *reinterpret_cast<float4*>(sStage + r * LDS_ + 4 * hl) = acc;  // h^{l+1}, fp32 (pooling, canonical inputs)
-            __align__(8) __nv_bfloat16 hi[4], lo[4];
-            tc05::split_bf16(acc.x, hi[0], lo[0]); tc05::split_bf16(acc.y, hi[1], lo[1]);
-            tc05::split_bf16(acc.z, hi[2], lo[2]); tc05::split_bf16(acc.w, hi[3], lo[3]);
-            const uint32_t off = tc05::sw128_offset(r, 4 * hl);
-            *reinterpret_cast<uint2*>(sAhi + off) = *reinterpret_cast<const uint2*>(hi);  // next layer's A operand
-            *reinterpret_cast<uint2*>(sAlo + off) = *reinterpret_cast<const uint2*>(lo);
+            if (code) {
+              const float* cv = sCvec + sRowG[r] * 2 * F + (code - 1) * F + 4 * q;
+              add4(a0, *reinterpret_cast<const float4*>(cv));
+              add4(a1, *reinterpret_cast<const float4*>(cv + 32));
+            }
+            a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a0.z = fmaxf(a0.z, 0.f); a0.w = fmaxf(a0.w, 0.f);
+            a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f); a1.z = fmaxf(a1.z, 0.f); a1.w = fmaxf(a1.w, 0.f);
+            float* dst = sStage + r * LDS_ + 4 * q;  // h^{l+1}, fp32 (pooling, canonical inputs)
+            *reinterpret_cast<float4*>(dst) = a0;
+            *reinterpret_cast<float4*>(dst + 32) = a1;
+            uint2 hi, lo;
+            split4(a0, hi, lo);
+            uint32_t off = tc05::sw128_offset(r, 4 * q);
+            *reinterpret_cast<uint2*>(sAhi + off) = hi;  // next layer's A operand
+            *reinterpret_cast<uint2*>(sAlo + off) = lo;
+            split4(a1, hi, lo);
+            off = tc05::sw128_offset(r, 32 + 4 * q);
+            *reinterpret_cast<uint2*>(sAhi + off) = hi;
+            *reinterpret_cast<uint2*>(sAlo + off) = lo;
           }
         }
         tc05::fence_proxy_async_smem();  // A images written through the generic proxy -> visible to tcgen05.mma
