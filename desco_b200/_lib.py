@@ -89,6 +89,8 @@ SIGNATURES = {
     "desco_partition_scan_workspace_bytes": (_L, [_I]),
     "desco_partition_scan": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
     "desco_partition_fill": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "desco_partition_batch_workspace_bytes": (_L, [_I]),
+    "desco_partition_batch": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _L, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP, _VP, _L, _VP, _VP]),
     "desco_partition_large_workspace_bytes": (_L, [_I, _I]),
     "desco_partition_large_count": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
     "desco_partition_large_fill": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
@@ -149,7 +151,11 @@ class DescoError(RuntimeError):
     pass
 
 
-_ERR = {-22: "EINVAL (bad argument)", -12: "ENOMEM", -5: "ECUDA (CUDA runtime error)", -34: "ERANGE (size limit exceeded)"}
+_ERR = {-22: "EINVAL (bad argument)", -12: "ENOMEM", -5: "ECUDA (CUDA runtime error)", -34: "ERANGE (size limit exceeded)",
+        -105: "ENOBUFS (output capacity too small)"}
+
+
+ENOBUFS = -105
 
 
 def check(code: int, what: str) -> None:

@@ -8,6 +8,7 @@
 #define DESCO_ENOMEM (-12)
 #define DESCO_ECUDA (-5)
 #define DESCO_ERANGE (-34)
+#define DESCO_ENOBUFS (-105)
 
 #define DESCO_CUDA_TRY(expr)                      \
   do {                                            \

@@ -1404,9 +1404,11 @@ __global__ void scan_finalize_kernel(const int32_t* __restrict__ centres, const 
                                      const int32_t* __restrict__ ne, const int32_t* __restrict__ rank,
                                      const int32_t* __restrict__ node_off, const int32_t* __restrict__ edge_off, int C,
                                      int32_t* __restrict__ nbh_ptr, int32_t* __restrict__ centre_out,
-                                     uint8_t* __restrict__ indicator, int32_t* __restrict__ totals) {
+                                     uint8_t* __restrict__ indicator, int32_t* __restrict__ totals,
+                                     int32_t* __restrict__ max_rows) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C) return;
+  const bool in = i < C;
+  if (!in) i = C - 1;  // keep the warp whole for the shuffle below; the duplicate work is idempotent
   bool keep = ne[i] > 0;
   if (indicator) indicator[i] = keep ? 1 : 0;
   if (keep) {
@@ -1419,6 +1421,12 @@ __global__ void scan_finalize_kernel(const int32_t* __restrict__ centres, const 
     totals[0] = G;
     totals[1] = V;
     totals[2] = E;
+  }
+  if (max_rows) {  // rows of the largest kept neighborhood (caller-zeroed)
+    int m = keep ? nv[i] : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(FULL_MASK, m, d));
+    if (lane_id() == 0 && m > 0) atomicMax(max_rows, m);
   }
 }
 
@@ -1512,9 +1520,136 @@ int desco_partition_scan(const int32_t* centres, const int32_t* nv, const int32_
   DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(workspace, bytes, ne, edge_off, num_centres, s));
   desco_count_launches(1);
   scan_finalize_kernel<<<(num_centres + 255) / 256, 256, 0, s>>>(centres, nv, ne, keep_rank, node_off, edge_off,
-                                                                num_centres, nbh_ptr, centre_out, indicator, totals);
+                                                                num_centres, nbh_ptr, centre_out, indicator, totals, nullptr);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// Pass 2 for batches of up to a few 10^4 centres in ONE single-CTA launch (instead of three cub scans + finalize =
+// seven launches): exclusive scans of (kept, rows, edges), the neighborhood pointers, indicator and totals.
+__global__ void __launch_bounds__(1024) scan_small_kernel(const int32_t* __restrict__ centres, const int32_t* __restrict__ nv,
+                                                          const int32_t* __restrict__ ne, int C, int32_t* __restrict__ node_off,
+                                                          int32_t* __restrict__ edge_off, int32_t* __restrict__ nbh_ptr,
+                                                          int32_t* __restrict__ centre_out, uint8_t* __restrict__ indicator,
+                                                          int32_t* __restrict__ totals) {
+  __shared__ int s_w[3][32];
+  __shared__ int s_carry[3];
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  if (tid < 3) s_carry[tid] = 0;
+  int mx = 0;
+  __syncthreads();
+  for (int base = 0; base < C; base += 1024) {
+    const int i = base + tid;
+    const int v = i < C ? nv[i] : 0, e = i < C ? ne[i] : 0, k = e > 0 ? 1 : 0;
+    int sk = warp_incl_scan(k), sv = warp_incl_scan(v), se = warp_incl_scan(e);
+    if (lane == 31) { s_w[0][warp] = sk; s_w[1][warp] = sv; s_w[2][warp] = se; }
+    __syncthreads();
+    if (warp < 3) {
+      const int x = s_w[warp][lane];
+      const int incl = warp_incl_scan(x);
+      s_w[warp][lane] = incl - x;  // exclusive base of warp `lane` for quantity `warp`
+    }
+    __syncthreads();
+    const int rk = s_carry[0] + s_w[0][warp] + sk - k;
+    const int no = s_carry[1] + s_w[1][warp] + sv - v;
+    const int eo = s_carry[2] + s_w[2][warp] + se - e;
+    if (i < C) {
+      node_off[i] = no;
+      edge_off[i] = eo;
+      if (indicator) indicator[i] = (uint8_t)k;
+      if (k) {
+        nbh_ptr[rk] = no;
+        centre_out[rk] = centres[i];
+        mx = max(mx, v);
+      }
+      if (i == C - 1) {
+        nbh_ptr[rk + k] = no + v;
+        totals[0] = rk + k;
+        totals[1] = no + v;
+        totals[2] = eo + e;
+      }
+    }
+    __syncthreads();
+    if (tid == 1023) { s_carry[0] = rk + k; s_carry[1] = no + v; s_carry[2] = eo + e; }
+    __syncthreads();
+  }
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 16));
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 8));
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 4));
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 2));
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 1));
+  if (lane == 0 && mx > 0) atomicMax(&totals[3], mx);
+}
+}  // namespace
+
+extern "C" {
+
+int64_t desco_partition_batch_workspace_bytes(int32_t num_centres) {
+  const int64_t c = num_centres > 0 ? num_centres : 1;
+  return ((5 * c * 4 + 255) / 256) * 256 + 256 + desco_partition_scan_workspace_bytes(num_centres);
+}
+
+int desco_partition_batch(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
+                          const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
+                          int32_t max_graph_nodes, void* workspace, int64_t workspace_bytes, int32_t* nbh_ptr,
+                          int32_t* centre_out, uint8_t* indicator, int32_t* centre_graph, int32_t* node_gid,
+                          int32_t* edge_ptr, int64_t cap_rows, int32_t* edge_col, uint8_t* edge_tri, int64_t cap_edges,
+                          int32_t* totals_host, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!totals_host || !nbh_ptr || num_centres < 0) return DESCO_EINVAL;
+  totals_host[0] = totals_host[1] = totals_host[2] = totals_host[3] = 0;
+  if (num_centres == 0) {
+    DESCO_CUDA_TRY(cudaMemsetAsync(nbh_ptr, 0, sizeof(int32_t), s));
+    return DESCO_OK;
+  }
+  if (!workspace || workspace_bytes < desco_partition_batch_workspace_bytes(num_centres) || !centre_out || !centre_graph)
+    return DESCO_EINVAL;
+  const size_t c = (size_t)num_centres;
+  int32_t* nv = (int32_t*)workspace;
+  int32_t* ne = nv + c;
+  int32_t* rank = ne + c;
+  int32_t* noff = rank + c;
+  int32_t* eoff = noff + c;
+  int32_t* small = (int32_t*)((char*)workspace + ((5 * c * 4 + 255) / 256) * 256);  // totals[3], max rows, status
+  void* scan_ws = (char*)small + 256;
+  const int64_t scan_bytes = desco_partition_scan_workspace_bytes(num_centres);
+  DESCO_CUDA_TRY(cudaMemsetAsync(small, 0, 256, s));
+  int rc = launch_partition(rowptr, col, graph_ptr, num_graphs, centres, num_centres, depth, mode, max_graph_nodes, nv, ne,
+                            centre_graph, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, small + 4, s);
+  if (rc) return rc;
+  desco_count_launches(1);
+  if (num_centres <= 65536) {
+    scan_small_kernel<<<1, 1024, 0, s>>>(centres, nv, ne, num_centres, noff, eoff, nbh_ptr, centre_out, indicator, small);
+  } else {
+    size_t bytes = (size_t)scan_bytes;
+    cub::TransformInputIterator<int, KeepFlag, const int32_t*> it(ne, KeepFlag());
+    DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_ws, bytes, it, rank, num_centres, s));
+    bytes = (size_t)scan_bytes;
+    DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_ws, bytes, nv, noff, num_centres, s));
+    bytes = (size_t)scan_bytes;
+    DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_ws, bytes, ne, eoff, num_centres, s));
+    scan_finalize_kernel<<<(num_centres + 255) / 256, 256, 0, s>>>(centres, nv, ne, rank, noff, eoff, num_centres, nbh_ptr,
+                                                                  centre_out, indicator, small, small + 3);
+  }
+  DESCO_LAUNCH_CHECK();
+  // the one host sync of the path: output sizes (and the device status word) through a pinned staging buffer
+  static thread_local int32_t* pinned = nullptr;
+  if (!pinned) DESCO_CUDA_TRY(cudaHostAlloc((void**)&pinned, 64, cudaHostAllocDefault));
+  DESCO_CUDA_TRY(cudaMemcpyAsync(pinned, small, 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  DESCO_CUDA_TRY(cudaStreamSynchronize(s));
+  for (int i = 0; i < 4; ++i) totals_host[i] = pinned[i];
+  if (pinned[4] != 0) return pinned[4];
+  if (pinned[1] > cap_rows || pinned[2] > cap_edges) return DESCO_ENOBUFS;  // caller re-allocates from totals_host
+  if (pinned[1] == 0) {
+    if (edge_ptr) DESCO_CUDA_TRY(cudaMemsetAsync(edge_ptr, 0, sizeof(int32_t), s));
+    return DESCO_OK;
+  }
+  if (!node_gid || !edge_ptr || !edge_col || !edge_tri) return DESCO_EINVAL;
+  return launch_partition(rowptr, col, graph_ptr, num_graphs, centres, num_centres, depth, mode, max_graph_nodes, nv, ne,
+                          centre_graph, 1, noff, eoff, node_gid, edge_ptr, edge_col, edge_tri, small + 4, s);
 }
 
 int desco_partition_fill(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,

@@ -16,6 +16,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Union
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -201,6 +203,8 @@ def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: in
     centres = centres.to(device=dev, dtype=torch.int32).contiguous()
     C = centres.numel()
     i32 = dict(dtype=torch.int32, device=dev)
+    if not large:
+        return _partition_batch_one_call(lib, graph, centres, C, depth, mode)
     scratch = torch.empty((6, max(C, 1)), **i32)  # nv, ne, centre_graph, keep_rank, node_off, edge_off
     nv, ne, cg, rank, noff, eoff = scratch.unbind(0)
     nbh_ptr = torch.empty(C + 1, **i32)
@@ -253,6 +257,47 @@ def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: in
     if large:
         batch._cache["tier"] = lwork[:C].clone()  # which tier served each centre (0 shared-memory hash, 1 team bitmap)
     return batch
+
+
+_CAPACITY = {"rows_per_centre": 24.0, "edges_per_row": 6.0}  # running maxima of the batches seen so far
+
+
+def _partition_batch_one_call(lib, graph: DeviceCSR, centres: torch.Tensor, C: int, depth: int, mode: int) -> NeighborhoodBatch:
+    """count -> scans -> (one stream sync for the sizes) -> fill inside ONE C call (``desco_partition_batch``).  The packed
+    batch is emitted into buffers sized from the largest rows-per-centre / edges-per-row ratios seen so far; the call
+    reports ENOBUFS with the exact sizes when they are too small and is then repeated once."""
+    dev = graph.rowptr.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    per = torch.empty((3, max(C, 1) + 1), **i32)  # nbh_ptr, centre_out, centre_graph
+    nbh_ptr, centre_out, cg = per[0], per[1, :max(C, 1)], per[2, :max(C, 1)]
+    indicator = torch.empty(max(C, 1), dtype=torch.uint8, device=dev)
+    wbytes = int(lib.desco_partition_batch_workspace_bytes(C))
+    work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    totals = (ctypes.c_int32 * 4)()
+    cap_rows = int(min(C * min(graph.max_graph_nodes, _CAPACITY["rows_per_centre"] * 1.25) + 64, 2**31 - 2))
+    cap_edges = int(min(cap_rows * _CAPACITY["edges_per_row"] * 1.25 + 64, 2**31 - 2))
+    with torch.cuda.device(dev):
+        st = _stream()
+        for attempt in range(2):
+            rows = torch.empty((2, cap_rows + 1), **i32)  # node_gid, edge_ptr
+            edge_col = torch.empty(cap_edges, **i32)
+            edge_tri = torch.empty(cap_edges, dtype=torch.uint8, device=dev)
+            rc = lib.desco_partition_batch(
+                _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres), C, depth, mode,
+                graph.max_graph_nodes, _ptr(work), wbytes, _ptr(nbh_ptr), _ptr(centre_out), _ptr(indicator), _ptr(cg),
+                _ptr(rows[0]), _ptr(rows[1]), cap_rows, _ptr(edge_col), _ptr(edge_tri), cap_edges, totals, st)
+            G, V, E, max_nv = (int(x) for x in totals)
+            if rc != _lib.ENOBUFS or attempt == 1:
+                break
+            cap_rows, cap_edges = V, E
+        _lib.check(rc, "desco_partition_batch")
+    if C and V:
+        _CAPACITY["rows_per_centre"] = max(_CAPACITY["rows_per_centre"], V / C)
+        _CAPACITY["edges_per_row"] = max(_CAPACITY["edges_per_row"], E / V)
+    return NeighborhoodBatch(
+        nbh_ptr[: G + 1], rows[0, :V], rows[1, : V + 1], edge_col[:E], edge_tri[:E], centre_out[:G], indicator[:C], cg[:C],
+        graph.graph_ptr, G, V, E, hetero=(mode == MODE_HETERO), max_rows=max_nv,
+    )
 
 
 def shmp_edge_types(edge_ptr: torch.Tensor, edge_col: torch.Tensor) -> torch.Tensor:

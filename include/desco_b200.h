@@ -4,7 +4,8 @@
  * The reference (fuvty/DeSCo @ 4508f7a) is 100 % Python and has no FFI of its own; every entry point below cites the
  * reference function(s) it replaces (paths relative to the reference root).  All pointers are DEVICE pointers unless
  * the name says host; sizes are element counts; `stream` is a cudaStream_t passed as void* (NULL = default stream).
- * Every function returns 0 on success or a negative errno-style code (DESCO_E*); nothing throws across the boundary.
+ * Every function returns 0 on success or a negative errno-style code (DESCO_E*: -22 EINVAL, -12 ENOMEM, -5 ECUDA,
+ * -34 ERANGE, -105 ENOBUFS); nothing throws across the boundary.
  * Kernels that detect a violated precondition on the device write a DESCO_E* code into `status` (device int32,
  * caller-zeroed) which the caller reads at its next synchronisation point.
  *
@@ -86,6 +87,21 @@ int desco_partition_fill(const int32_t* rowptr, const int32_t* col, const int32_
                          int32_t max_graph_nodes, const int32_t* nv, const int32_t* ne, const int32_t* centre_graph,
                          const int32_t* node_off, const int32_t* edge_off, int32_t* node_gid, int32_t* edge_ptr,
                          int32_t* edge_col, uint8_t* edge_tri, int32_t* status, void* stream);
+
+/* Passes 1-3 in ONE call (what NeighborhoodDataset.process does per dataset, workload.py:215-294): count, scans, one
+ * stream synchronisation to read the output sizes, fill.  The caller owns every buffer: `workspace`
+ * (desco_partition_batch_workspace_bytes), the per-centre outputs (nbh_ptr[num_centres+1], centre_out / indicator /
+ * centre_graph [num_centres]) and the packed batch at a capacity of its choice (node_gid[cap_rows],
+ * edge_ptr[cap_rows+1], edge_col / edge_tri [cap_edges]).  totals_host[4] (host memory) receives {G, V, E, rows of the
+ * largest neighborhood}.  Returns DESCO_ENOBUFS, with totals_host filled and nothing emitted, when V > cap_rows or
+ * E > cap_edges: re-allocate and call again. */
+int64_t desco_partition_batch_workspace_bytes(int32_t num_centres);
+int desco_partition_batch(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
+                          const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
+                          int32_t max_graph_nodes, void* workspace, int64_t workspace_bytes, int32_t* nbh_ptr,
+                          int32_t* centre_out, uint8_t* indicator, int32_t* centre_graph, int32_t* node_gid,
+                          int32_t* edge_ptr, int64_t cap_rows, int32_t* edge_col, uint8_t* edge_tri, int64_t cap_edges,
+                          int32_t* totals_host, void* stream);
 
 /* Large-graph variants of passes 1 and 3 (config 5: a 10M-node / 200M-directed-edge target, whose node bitsets no
  * longer fit shared memory; desco_partition_count returns DESCO_ERANGE there).  Same outputs, same reference
