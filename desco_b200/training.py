@@ -298,7 +298,16 @@ class _TrainForward(torch.autograd.Function):
         dev = params[0].device
         with torch.cuda.device(dev), torch.no_grad():
             ops.st = _stream()
-            grads = {p: torch.zeros_like(p, memory_format=torch.contiguous_format) for p in params}
+            # gradients of this step: one flat zeroed buffer.  When the parameters' .grad are the views of a FusedAdam
+            # flat buffer with the same layout, backward() adds the whole buffer into it with ONE launch (instead of a
+            # fill, a scale and an accumulate per parameter = ~600 launches for the 200 tensors of the model).
+            opt = _flat_optimizer(params)
+            sizes = [p.numel() for p in params]
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            grads, off = {}, 0
+            for p, k in zip(params, sizes):
+                grads[p] = flat[off:off + k].view(p.shape)
+                off += k
             G = batch.num_neighborhoods
             tape_t = _ShmpTape(model.emb_model, batch, ops)
             tape_q = _ShmpTape(model.emb_model_query, model.query_loader, ops)
@@ -332,12 +341,32 @@ class _TrainForward(torch.autograd.Function):
             ops.dgrad(dBq, lin1.weight[:, F:], d_q)
             tape_t.backward(d_t, grads)
             tape_q.backward(d_q, grads)
-        ctx.grads = [grads[p] for p in params]
+        ctx.flat, ctx.opt, ctx.shapes, ctx.sizes = flat, opt, [p.shape for p in params], sizes
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
-        return (None, None, None) + tuple(g * grad_out for g in ctx.grads)
+        if ctx.opt is not None and ctx.opt.owns_grads():
+            ctx.opt.flat_g.addcmul_(ctx.flat, grad_out.to(torch.float32))  # p.grad += dL/dp for every parameter at once
+            return (None, None, None) + (None,) * len(ctx.sizes)
+        scaled = ctx.flat * grad_out
+        out, off = [], 0
+        for shape, k in zip(ctx.shapes, ctx.sizes):
+            out.append(scaled[off:off + k].view(shape))
+            off += k
+        return (None, None, None) + tuple(out)
+
+
+def _flat_optimizer(params):
+    """The FusedAdam whose flat gradient buffer lays these parameters out in this order, or None."""
+    opt, off = None, 0
+    for p in params:
+        tag = getattr(p, "_desco_flat", None)
+        if tag is None or (opt is not None and tag[0] is not opt) or tag[1] != off:
+            return None
+        opt = tag[0]
+        off += p.numel()
+    return opt if opt is not None and off == opt.flat_g.numel() else None
 
 
 def train_forward(model, batch: NeighborhoodBatch, y: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -383,9 +412,14 @@ class FusedAdam(torch.optim.Optimizer):
                 if p.grad is not None:
                     gv.copy_(p.grad)
                 p.grad = gv
+                p._desco_flat = (self, off)
                 self._views.append(gv)
                 off += k
         self.step_count = 0
+
+    def owns_grads(self) -> bool:
+        """True while every parameter's .grad still is its view of the flat gradient buffer."""
+        return all(p.grad is not None and p.grad.data_ptr() == gv.data_ptr() for p, gv in zip(self._params, self._views))
 
     def zero_grad(self, set_to_none: bool = False):
         self.flat_g.zero_()
