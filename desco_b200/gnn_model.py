@@ -323,7 +323,14 @@ def pack_gossip_weights(base: "GossipBaseGNN") -> Dict[str, torch.Tensor]:
           d(base.post_mp[5].weight).t().contiguous().flatten(), d(base.post_mp[5].bias),
           d(base.post_mp[7].weight)[0], d(base.post_mp[7].bias), pad3]
     f32 = lambda parts: torch.cat(parts).to(torch.float32).to(dev).contiguous()
-    out = {"wq": f32(wq), "wg": f32(wg)}
+    # tensor-core operand images of the four GEMMs of the layer-1 / post_mp chain (csrc/gossip.cu IMG_*): B operand
+    # W[n, k] per 64-wide K block, bf16 hi rows then lo rows, appended to the blob as raw bytes
+    Wx2 = torch.cat([(Wup1a @ Wcom1).t(), Wup1b.t()], 0).t()  # [64 n][128 k]
+    Wy1 = torch.cat([P0x1.t(), P0x2.t()], 0).t()
+    images = torch.cat([pack_b_operand(Wx2[:, :F]), pack_b_operand(Wx2[:, F:]), pack_b_operand(Wy1[:, :F]),
+                        pack_b_operand(Wy1[:, F:]), pack_b_operand(d(base.post_mp[3].weight)),
+                        pack_b_operand(d(base.post_mp[5].weight))])
+    out = {"wq": f32(wq), "wg": torch.cat([f32(wg), images.view(torch.float32).to(dev)]).contiguous()}
     lib = _lib.load()
     assert out["wq"].numel() == lib.desco_gossip_query_weight_floats(), (out["wq"].numel(), lib.desco_gossip_query_weight_floats())
     assert out["wg"].numel() == lib.desco_gossip_weight_floats(), (out["wg"].numel(), lib.desco_gossip_weight_floats())
@@ -344,7 +351,7 @@ class GossipBaseGNN(_PackedWeightsMixin, nn.Module):
             nn.Linear(p, hidden_dim), nn.Dropout(args.dropout), nn.LeakyReLU(0.1), nn.Linear(hidden_dim, hidden_dim),
             nn.ReLU(), nn.Linear(hidden_dim, 256), nn.ReLU(), nn.Linear(256, output_dim),
         )
-        self.precision = "fp32"
+        self.precision = "bf16x3"  # tcgen05 layer-1 / post_mp chain (fp32-grade products); "fp32" = FFMA kernel
         self._init_cache()
 
     def packed_weights(self):

@@ -205,6 +205,9 @@ int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const f
  * the counts of its halo have been exchanged:  prepare_queries -> layer0 (any node range; needs x of the
  * neighbours) -> layer1 (needs s4 of the neighbours).  qvec: [Q, 256] floats, s4: [N, Q, 4] floats.
  * ---------------------------------------------------------------------------------------------------------------- */
+/* Profiling aid: clock64 cycles thread 0 of every CTA of the tensor-core layer-1 kernel spent per phase since the last
+ * reset (out[6]: gather, hub rows, x2, y1, y2, y4 GEMM + epilogue). */
+int desco_gossip_tc_phase_cycles(uint64_t* out, int32_t reset);
 int64_t desco_gossip_weight_floats(void);
 int64_t desco_gossip_query_weight_floats(void);
 int64_t desco_gossip_workspace_bytes(int32_t num_nodes, int32_t num_queries);

@@ -13,7 +13,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def _pair(seed):
+@pytest.fixture(params=["bf16x3", "fp32"])
+def precision(request):
+    """bf16x3: tcgen05 layer-1 / post_mp chain (three-pass bf16 hi/lo split, the default); fp32: the FFMA kernel.
+    Both must meet the same 1e-4 bar."""
+    return request.param
+
+
+def _pair(seed, precision="bf16x3"):
     from desco_b200.lightning_model import GossipCountingModel
     from oracle import model as M
 
@@ -21,6 +28,7 @@ def _pair(seed):
     om = M.GossipCountingModel()
     pm = GossipCountingModel()
     pm.emb_model.load_state_dict(om.emb_model.state_dict())
+    pm.emb_model.precision = precision
     return om, pm.cuda()
 
 
@@ -37,7 +45,7 @@ def _rel(a, b):
     return ((a - b).abs() / b.abs().clamp(min=1.0)).max().item()
 
 
-def test_gossip_matches_reference_golden(cuda_device, golden_dir):
+def test_gossip_matches_reference_golden(cuda_device, golden_dir, precision):
     from desco_b200.lightning_model import GossipCountingModel
     from oracle import model as M
 
@@ -46,6 +54,7 @@ def test_gossip_matches_reference_golden(cuda_device, golden_dir):
     om = M.GossipCountingModel()  # same seeded construction order as the reference BaseGNN (checked in the CPU suite)
     pm = GossipCountingModel()
     pm.emb_model.load_state_dict(om.emb_model.state_dict())
+    pm.emb_model.precision = precision
     pm = pm.cuda()
     csr = TargetCSR(z["rowptr"], z["col"], z["graph_ptr"])
     out = _run(pm, csr, torch.from_numpy(z["x"]), torch.from_numpy(z["query_emb"]))
@@ -56,8 +65,8 @@ def test_gossip_matches_reference_golden(cuda_device, golden_dir):
 
 @pytest.mark.parametrize("gen,kw,Q", [(gen_mutag_shaped, dict(num_graphs=60), 29), (gen_enzymes_shaped, dict(num_graphs=50), 29),
                                        (gen_imdb_shaped, dict(num_graphs=40), 5), (gen_imdb_shaped, dict(num_graphs=10), 40)])
-def test_gossip_matches_oracle(cuda_device, gen, kw, Q):
-    om, pm = _pair(7)
+def test_gossip_matches_oracle(cuda_device, gen, kw, Q, precision):
+    om, pm = _pair(7, precision)
     csr = gen(seed=8, **kw)
     g = torch.Generator().manual_seed(9)
     x = torch.floor(torch.exp(torch.randn(csr.num_nodes, Q, generator=g)))
@@ -69,8 +78,8 @@ def test_gossip_matches_oracle(cuda_device, gen, kw, Q):
     assert _rel(out, ref) <= TOL
 
 
-def test_gossip_powerlaw_hubs(cuda_device):
-    om, pm = _pair(10)
+def test_gossip_powerlaw_hubs(cuda_device, precision):
+    om, pm = _pair(10, precision)
     csr = gen_powerlaw(4000, 30000, seed=3)
     g = torch.Generator().manual_seed(4)
     Q = 8
@@ -83,12 +92,12 @@ def test_gossip_powerlaw_hubs(cuda_device):
     assert _rel(out, ref) <= TOL
 
 
-def test_gossip_zero_counts_and_isolated_nodes(cuda_device):
+def test_gossip_zero_counts_and_isolated_nodes(cuda_device, precision):
     import networkx as nx
 
     from desco_b200.graph import csr_from_networkx
 
-    om, pm = _pair(11)
+    om, pm = _pair(11, precision)
     g = nx.Graph()
     g.add_nodes_from(range(5))
     g.add_edge(1, 3)
@@ -102,12 +111,14 @@ def test_gossip_zero_counts_and_isolated_nodes(cuda_device):
     assert _rel(out, ref) <= TOL
 
 
-def test_gossip_sharded_node_ranges_equal_full(cuda_device):
+def test_gossip_sharded_node_ranges_equal_full(cuda_device, precision):
     """The three-stage C ABI on node ranges (what each rank runs after the count all-gather) == the single call."""
     from desco_b200 import _lib
     from desco_b200.data import DeviceCSR, _ptr, _stream
 
-    _, pm = _pair(12)
+    from desco_b200.gnn_model import PRECISION
+
+    _, pm = _pair(12, precision)
     csr = gen_enzymes_shaped(seed=13, num_graphs=80)
     d = DeviceCSR.from_host(csr)
     N, Q = csr.num_nodes, 29
@@ -127,6 +138,6 @@ def test_gossip_sharded_node_ranges_equal_full(cuda_device):
     assert lib.desco_gossip_layer0(_ptr(d.rowptr), _ptr(d.col), 0, N, _ptr(x), Q, _ptr(qvec), _ptr(s4), st) == 0
     cuts = [0, N // 3, N // 3 + 77, N]
     for a, b in zip(cuts[:-1], cuts[1:]):
-        assert lib.desco_gossip_layer1(_ptr(d.rowptr), _ptr(d.col), a, b, _ptr(s4), Q, _ptr(qvec), _ptr(w["wg"]), _ptr(out), 0, st) == 0
+        assert lib.desco_gossip_layer1(_ptr(d.rowptr), _ptr(d.col), a, b, _ptr(s4), Q, _ptr(qvec), _ptr(w["wg"]), _ptr(out), PRECISION[precision], st) == 0
     torch.cuda.synchronize()
     assert torch.equal(out, full)
