@@ -109,7 +109,8 @@ SIGNATURES = {
     "desco_gossip_workspace_bytes": (_L, [_I, _I]),
     "desco_gossip_prepare_queries": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "desco_gossip_layer0": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP]),
-    "desco_gossip_layer1": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP]),
+    "desco_gossip_layer1": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP, _L, _VP]),
+    "desco_gossip_layer1_workspace_bytes": (_L, [_I, _I, _I]),
     "desco_shmp_fused_phase_cycles": (_I, [_VP, _I]),
     "desco_train_plan": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "desco_train_aggregate": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP, _I, _VP, _I, _VP, _I, _VP, _I, _VP]),

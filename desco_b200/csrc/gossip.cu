@@ -299,33 +299,201 @@ __global__ void __launch_bounds__(THREADS, 2) gossip_layer1_kernel(
 // ------------------------------------------------------------------------------------------------------------------
 // Tensor-core variant of layer 1 + post_mp (DESCO_PRECISION_BF16X3).  Per (node, query) the chain is 36.9 k MACs of
 // dense GEMM (x2: 128->64, y1: 128->64, y2: 64->64, y3: 64->256) against a few hundred flops of gather, so the FFMA
-// kernel above is compute bound on the CUDA cores; here the four GEMMs of a 128-node tile run on tcgen05 (M = 128,
-// accumulators in TMEM, bf16 hi/lo split in three passes = fp32-grade products) with all four weight matrices resident
-// in shared memory as ready-made operand images (144 KB, one bulk copy per CTA), and the activations never leave the
-// chip: every epilogue reads its accumulator with tcgen05.ld, applies bias / rank-1 terms / activation and writes the
-// next GEMM's A operand (swizzled bf16 hi/lo) in place of an operand that is dead by then (two 32 KB slots suffice).
+// kernel above is compute bound on the CUDA cores.  Here the work is split by what bounds it:
+//   * gossip_gather_kernel - the gated sweep (dependent col[] -> S4[] loads, ~1 us each): small CTAs at high occupancy.
+//     A CTA owns a tile = 128 consecutive nodes x 1 query, recomputes x1_j per neighbour and writes the tile's u and x1
+//     rows to a staging buffer AS the bf16 hi/lo SWIZZLE_128B operand images the tensor core wants (64 KB per tile);
+//   * gossip_chain_kernel - persistent, one CTA per SM: the four weight matrices stay resident in shared memory as
+//     operand images (144 KB, bulk-copied once), a tile's two operand slots arrive by bulk async copy (the next tile's
+//     are issued as soon as a slot is dead, under the running tile's epilogues), the four GEMMs run on tcgen05 (M = 128,
+//     accumulators in TMEM, three hi/lo passes = fp32-grade products) and every epilogue reads its accumulator with
+//     tcgen05.ld, applies bias / rank-1 terms / activation and writes the next GEMM's A operand in place of a dead one.
+// The staging buffer is walked in chunks of tiles, so its size is bounded whatever the graph.
 // ------------------------------------------------------------------------------------------------------------------
 namespace gtc {
 constexpr int TR = 128;
+constexpr int SLOT = 2 * TR * 128;               // one operand slot: hi (16 KB) | lo (16 KB)
+constexpr int TILE_CD = 2 * TR * 4;              // c[TR], d1[TR]
+constexpr int TILE_BYTES = 2 * SLOT + TILE_CD;   // staging per tile: u slot | x1 slot | c | d1
+constexpr int HUB_DEG = 512;                     // rows with more neighbours are gathered by the whole CTA
+
+// ---------------------------------------------------------------- gather ----------------------------------------
+constexpr int G_THREADS = 256;
+constexpr int G_NW = G_THREADS / 32;
+constexpr int GR = 2;  // rows whose loads are in flight together (more = more code: the kernel is I-cache sensitive)
+
+__global__ void __launch_bounds__(G_THREADS, 3) gossip_gather_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int node_begin, int node_end,
+    const float4* __restrict__ S4, int Q, const float* __restrict__ qvec, const float* __restrict__ wg, long long tile0,
+    uint8_t* __restrict__ stage) {
+  __shared__ float4 s_slot[G_NW * 32];  // per-warp staging of 32 neighbours / per-warp partial sums of a hub row
+  __shared__ uint8_t s_hubs[TR];
+  __shared__ int s_nhub;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long tile = tile0 + blockIdx.x;
+  const int q = (int)(tile % Q);
+  const int i0 = node_begin + (int)(tile / Q) * TR;
+  uint8_t* gA0 = stage + (size_t)blockIdx.x * TILE_BYTES;  // u
+  uint8_t* gA1 = gA0 + SLOT;                               // x1
+  float* g_c = reinterpret_cast<float*>(gA1 + SLOT);
+  float* g_d1 = g_c + TR;
+  const float* qv = qvec + (size_t)q * QV;
+  const float g1 = qv[3 * F + 1];
+  const float2 alpha = *reinterpret_cast<const float2*>(qv + 2 * lane);
+  const float2 gamma = *reinterpret_cast<const float2*>(qv + F + 2 * lane);
+  const float2 beta = *reinterpret_cast<const float2*>(wg + WG_BETA + 2 * lane);
+  const float2 delta = *reinterpret_cast<const float2*>(wg + WG_DELTA + 2 * lane);
+  auto x1_of = [&](const float4 s) {
+    float2 r;
+    r.x = fmaxf(fmaf(s.x, alpha.x, fmaf(s.y, beta.x, fmaf(s.z, delta.x, gamma.x))), 0.f);
+    r.y = fmaxf(fmaf(s.x, alpha.y, fmaf(s.y, beta.y, fmaf(s.z, delta.y, gamma.y))), 0.f);
+    return r;
+  };
+  // 32 adjacency entries of a row starting at `base`, in two steps so that the loads of several rows are in flight
+  // together: fetch = every lane loads one neighbour's scalars; consume = the lanes park them in the warp's slot and all
+  // walk it (one broadcast 16-byte shared load per neighbour), recomputing their two features of x1_j.  The row is
+  // sorted, so the j < i neighbours are a prefix: no per-edge compare.
+  struct Fetch { int j; float4 s; int n; };
+  auto fetch = [&](int base, int ee) {
+    Fetch f;
+    const int e = base + lane;
+    f.j = 0x7fffffff;
+    f.s = make_float4(0.f, 0.f, 0.f, 0.f);
+    f.n = max(0, min(32, ee - base));
+    if (e < ee) {
+      f.j = col[e];
+      f.s = S4[(size_t)f.j * Q + q];
+    }
+    return f;
+  };
+  auto consume = [&](const Fetch& f, int i, float2& lt, float2& gt) {
+    float4* slot = s_slot + warp * 32;
+    slot[lane] = f.s;
+    const int n = f.n;
+    const int nlt = __popc(__ballot_sync(FULL_MASK, f.j < i));
+    __syncwarp();
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+    int k = 0;
+    for (; k + 1 < nlt; k += 2) {
+      const float2 v0 = x1_of(slot[k]), v1 = x1_of(slot[k + 1]);
+      a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
+    }
+    if (k < nlt) { const float2 v = x1_of(slot[k]); a0.x += v.x; a0.y += v.y; }
+    lt.x += a0.x + a1.x; lt.y += a0.y + a1.y;
+    a0 = make_float2(0.f, 0.f); a1 = a0;
+    for (k = nlt; k + 1 < n; k += 2) {
+      const float2 v0 = x1_of(slot[k]), v1 = x1_of(slot[k + 1]);
+      a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
+    }
+    if (k < n) { const float2 v = x1_of(slot[k]); a0.x += v.x; a0.y += v.y; }
+    gt.x += a0.x + a1.x; gt.y += a0.y + a1.y;
+    __syncwarp();
+  };
+  auto store_row = [&](uint8_t* img, int r, float2 v) {  // two features of row r as bf16 hi / lo, swizzled
+    const uint32_t off = tc05::sw128_offset(r, 2 * lane);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+    const float2 f = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v.x - f.x, v.y - f.y);
+    *reinterpret_cast<__nv_bfloat162*>(img + off) = h;
+    *reinterpret_cast<__nv_bfloat162*>(img + TR * 128 + off) = l;
+  };
+  if (tid == 0) s_nhub = 0;
+  __syncthreads();
+
+  // ---- x1_i and u_i = g1 * sum_{j<i} x1_j + (1-g1) * sum_{j>i} x1_j; one warp per row, hub rows deferred ----
+#pragma unroll 1
+  for (int r0 = warp; r0 < TR; r0 += G_NW * GR) {
+    int eb[GR], ee[GR];
+    bool hub[GR];
+    Fetch f[GR];
+#pragma unroll
+    for (int k = 0; k < GR; ++k) {
+      const int i = i0 + r0 + G_NW * k;
+      eb[k] = ee[k] = 0;
+      if (i < node_end) { eb[k] = rowptr[i]; ee[k] = rowptr[i + 1]; }
+    }
+#pragma unroll
+    for (int k = 0; k < GR; ++k) {
+      hub[k] = ee[k] - eb[k] > HUB_DEG;
+      if (hub[k]) {
+        if (lane == 0) s_hubs[atomicAdd(&s_nhub, 1)] = (uint8_t)(r0 + G_NW * k);
+        ee[k] = eb[k];
+      }
+      f[k] = fetch(eb[k], ee[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < GR; ++k) {
+      const int r = r0 + G_NW * k, i = i0 + r;
+      float2 u = make_float2(0.f, 0.f), x1 = u;
+      float c = 0.f, d1 = 0.f;
+      if (i < node_end) {
+        const float4 own = S4[(size_t)i * Q + q];
+        x1 = x1_of(own);
+        c = own.z;
+        d1 = own.w;
+        float2 lt = make_float2(0.f, 0.f), gt = lt;
+        Fetch cur = f[k];
+#pragma unroll 1
+        for (int base = eb[k] + 32; base < ee[k]; base += 32) {  // longer rows: the next 32 entries load under this batch
+          const Fetch nxt = fetch(base, ee[k]);
+          consume(cur, i, lt, gt);
+          cur = nxt;
+        }
+        consume(cur, i, lt, gt);
+        u.x = g1 * lt.x + (1.f - g1) * gt.x;
+        u.y = g1 * lt.y + (1.f - g1) * gt.y;
+      }
+      if (!hub[k]) store_row(gA0, r, u);
+      store_row(gA1, r, x1);
+      if (lane == 0) {
+        g_c[r] = c;
+        g_d1[r] = d1;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- hub rows: 32-edge chunks dealt over all warps of the CTA, partial sums added in warp order ----
+  for (int h = 0, nh = s_nhub; h < nh; ++h) {
+    const int r = s_hubs[h], i = i0 + r;
+    const int eb = rowptr[i], ee = rowptr[i + 1];
+    float2 lt = make_float2(0.f, 0.f), gt = lt;
+    for (int base = eb + 32 * warp; base < ee; base += 32 * G_NW * GR) {
+      Fetch f[GR];
+#pragma unroll
+      for (int k = 0; k < GR; ++k) f[k] = fetch(base + 32 * G_NW * k, ee);
+#pragma unroll
+      for (int k = 0; k < GR; ++k) consume(f[k], i, lt, gt);
+    }
+    s_slot[warp * 32 + lane] = make_float4(lt.x, lt.y, gt.x, gt.y);  // (consume ends with a __syncwarp: the slot is free)
+    __syncthreads();
+    if (warp == 0) {
+      float4 t = s_slot[lane];
+      for (int w = 1; w < G_NW; ++w) {
+        const float4 o = s_slot[w * 32 + lane];
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+      }
+      store_row(gA0, r, make_float2(g1 * t.x + (1.f - g1) * t.z, g1 * t.y + (1.f - g1) * t.w));
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- GEMM chain ------------------------------------
 constexpr int THREADS_TC = 512;
-constexpr int NW = THREADS_TC / 32;
 constexpr int ISSUER = THREADS_TC - 32;
 constexpr int SM_B = 0;
-constexpr int SM_A0 = SM_B + IMG_BYTES;          // hi (16 KB) | lo (16 KB)
-constexpr int SM_A1 = SM_A0 + 2 * TR * 128;
-constexpr int SM_VEC = SM_A1 + 2 * TR * 128;     // v1, b_up1, theta, b1 [64 each], b2, p3 [256 each], eta [64]
-constexpr int SM_C = SM_VEC + (4 * F + 2 * 4 * F + F) * 4;
-constexpr int SM_D1 = SM_C + TR * 4;
-constexpr int SM_PART = SM_D1 + TR * 4;          // [4][TR]
-constexpr int SM_HUBP = SM_PART + 4 * TR * 4;    // [NW][32] float4: per-warp partial (lt, gt) sums of a hub row
-constexpr int SM_HUBS = SM_HUBP + NW * 32 * 16;  // [TR] uint8 hub rows of the tile + counter
-constexpr int SM_BARS = SM_HUBS + TR + 16;
+constexpr int SM_A0 = SM_B + IMG_BYTES;          // u -> x2 -> y1
+constexpr int SM_A1 = SM_A0 + SLOT;              // x1 -> y2
+constexpr int SM_CD = SM_A1 + SLOT;              // c[TR], d1[TR] of the tile (arrive with the u slot)
+constexpr int SM_VEC = SM_CD + TILE_CD;          // v1, b_up1, theta, b1 [64 each], b2, p3 [256 each], eta [64]
+constexpr int SM_PART = SM_VEC + (4 * F + 2 * 4 * F + F) * 4;  // [4][TR]
+constexpr int SM_BARS = SM_PART + 4 * TR * 4;
 constexpr int SM_TOTAL = SM_BARS + 64;
-constexpr int HUB_DEG = 64;                      // rows with more neighbours are gathered by the whole CTA
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 static_assert(SMEM_BYTES <= 232448, "gossip tensor-core kernel exceeds the 227 KB shared-memory limit");
 static_assert(SM_A0 % 1024 == 0 && SM_A1 % 1024 == 0 && IMG_W2 % 1024 == 0 && IMG_P1 % 1024 == 0 && IMG_P2 % 1024 == 0,
               "UMMA tiles must be 1024-B aligned");
+static_assert(SM_CD % 16 == 0 && TILE_BYTES % 16 == 0, "bulk copies need 16-byte alignment");
 
 // 8 consecutive fp32 -> one 16-byte chunk of bf16 hi and one of lo
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
@@ -343,18 +511,19 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
 }
 
 // phase timing (thread 0 of every CTA adds its clock64 deltas; read with desco_gossip_tc_phase_cycles)
-enum { GPH_GATHER = 0, GPH_HUBS, GPH_X2, GPH_Y1, GPH_Y2, GPH_Y4, GPH_COUNT };
+enum { GPH_LOAD = 0, GPH_X2, GPH_Y1, GPH_Y2, GPH_Y4, GPH_SPARE, GPH_COUNT };
 __device__ unsigned long long g_phase_cycles[GPH_COUNT];
 
-__global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
-    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int node_begin, int node_end,
-    const float4* __restrict__ S4, int Q, const float* __restrict__ qvec, const float* __restrict__ wg,
-    float* __restrict__ out) {
+__global__ void __launch_bounds__(THREADS_TC, 1) gossip_chain_kernel(
+    int node_begin, int node_end, int Q, const float* __restrict__ qvec, const float* __restrict__ wg, long long tile0,
+    int num_tiles, const uint8_t* __restrict__ stage, float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem + SM_B;
   uint8_t* sA0 = smem + SM_A0;
   uint8_t* sA1 = smem + SM_A1;
+  float* s_c = reinterpret_cast<float*>(smem + SM_CD);
+  float* s_d1 = s_c + TR;
   float* sV1 = reinterpret_cast<float*>(smem + SM_VEC);
   float* sBup1 = sV1 + F;
   float* sTheta = sBup1 + F;
@@ -362,22 +531,15 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
   float* sB2 = sB1 + F;
   float* sP3 = sB2 + 4 * F;
   float* sEta = sP3 + 4 * F;
-  float* s_c = reinterpret_cast<float*>(smem + SM_C);
-  float* s_d1 = reinterpret_cast<float*>(smem + SM_D1);
   float* s_part = reinterpret_cast<float*>(smem + SM_PART);
-  float4* s_hubp = reinterpret_cast<float4*>(smem + SM_HUBP);
-  uint8_t* s_hubs = smem + SM_HUBS;
-  int* s_nhub = reinterpret_cast<int*>(smem + SM_HUBS + TR);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);  // [0] weights landed, [1] MMA done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);  // [0] weights, [1] MMA done, [2] u slot + c/d1, [3] x1 slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long tiles = (((long long)(node_end - node_begin) + TR - 1) / TR) * Q;
-  if ((long long)blockIdx.x >= tiles) return;
+  if ((int)blockIdx.x >= num_tiles) return;
 
   if (tid == 0) {
-    tc05::mbar_init(&bars[0], 1);
-    tc05::mbar_init(&bars[1], 1);
+    for (int b = 0; b < 4; ++b) tc05::mbar_init(&bars[b], 1);
     tc05::fence_mbar_init();
   }
   if (warp == 0) tc05::tmem_alloc(tmem_slot, 512);
@@ -385,10 +547,25 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
   __syncthreads();
   tc05::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  if (tid == ISSUER) {  // all four weight images, once per CTA
+  auto load_u = [&](int t) {  // ISSUER only: u slot + c/d1 of tile t (contiguous in the staging buffer apart from the x1 slot)
+    const uint8_t* src = stage + (size_t)t * TILE_BYTES;
+    tc05::mbar_arrive_expect_tx(&bars[2], SLOT + TILE_CD);
+    tc05::bulk_g2s(sA0, src, 16384, &bars[2]);
+    tc05::bulk_g2s(sA0 + 16384, src + 16384, 16384, &bars[2]);
+    tc05::bulk_g2s(s_c, src + 2 * SLOT, TILE_CD, &bars[2]);
+  };
+  auto load_x1 = [&](int t) {
+    const uint8_t* src = stage + (size_t)t * TILE_BYTES + SLOT;
+    tc05::mbar_arrive_expect_tx(&bars[3], SLOT);
+    tc05::bulk_g2s(sA1, src, 16384, &bars[3]);
+    tc05::bulk_g2s(sA1 + 16384, src + 16384, 16384, &bars[3]);
+  };
+  if (tid == ISSUER) {  // all four weight images once per CTA, then the first tile's operands
     const uint8_t* img = reinterpret_cast<const uint8_t*>(wg + WG_TC);
     tc05::mbar_arrive_expect_tx(&bars[0], IMG_BYTES);
     for (int off = 0; off < IMG_BYTES; off += 16384) tc05::bulk_g2s(sB + off, img + off, 16384, &bars[0]);
+    load_u(blockIdx.x);
+    load_x1(blockIdx.x);
   }
   for (int i = tid; i < 4 * F; i += THREADS_TC) {
     sB2[i] = wg[WG_B2 + i];
@@ -401,16 +578,14 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
     }
   }
   const float b3 = wg[WG_B3];
-  const float2 beta = *reinterpret_cast<const float2*>(wg + WG_BETA + 2 * lane);
-  const float2 delta = *reinterpret_cast<const float2*>(wg + WG_DELTA + 2 * lane);
   const uint32_t idesc64 = tc05::make_idesc_bf16(TR, F), idesc256 = tc05::make_idesc_bf16(TR, 4 * F);
-  uint32_t mphase = 0;
+  uint32_t mphase = 0, lphase = 0;
   bool weights_ready = false;  // meaningful in the ISSUER thread only
   const int qd = warp & 3, cg = warp >> 2;  // TMEM lane quarter / column group of this warp
   const int row = 32 * qd + lane;
   const uint32_t tlane = static_cast<uint32_t>(32 * qd) << 16;
 
-  // one GEMM: D[tmem + dcol] = sum over K blocks (A image, B image) and the three hi/lo passes
+  // one GEMM: D[tmem + dcol] = sum over K blocks (A slot, B image) and the three hi/lo passes
   auto issue = [&](uint32_t dcol, uint32_t idesc, const uint8_t* a0, const uint8_t* b0, int bpart0, const uint8_t* a1,
                    const uint8_t* b1, int bpart1) {
     // a*: A slot (hi at +0, lo at +TR*128); b*: B image of the K block (hi at +0, lo at +bpart bytes)
@@ -456,20 +631,13 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
     __syncthreads();
   };
 
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const long long tile = tile0 + t;
     const int q = (int)(tile % Q);
     const int i0 = node_begin + (int)(tile / Q) * TR;
+    const int tn = t + gridDim.x;  // this CTA's next tile
     const float* qv = qvec + (size_t)q * QV;
-    const float g1 = qv[3 * F + 1];
-    const float2 alpha = *reinterpret_cast<const float2*>(qv + 2 * lane);
-    const float2 gamma = *reinterpret_cast<const float2*>(qv + F + 2 * lane);
-    auto x1_of = [&](const float4 s) {
-      float2 r;
-      r.x = fmaxf(fmaf(s.x, alpha.x, fmaf(s.y, beta.x, fmaf(s.z, delta.x, gamma.x))), 0.f);
-      r.y = fmaxf(fmaf(s.x, alpha.y, fmaf(s.y, beta.y, fmaf(s.z, delta.y, gamma.y))), 0.f);
-      return r;
-    };
-    __syncthreads();  // previous tile fully retired (s_c, s_part, sEta)
+    __syncthreads();  // previous tile fully retired (s_part, sEta)
     long long tick = clock64();
     auto lap = [&](int phase) {
       if (tid == 0) {
@@ -479,141 +647,12 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
       }
     };
     if (tid < F) sEta[tid] = qv[2 * F + tid];
-    if (tid == 0) *s_nhub = 0;
-    __syncthreads();
-    // 32 adjacency entries of a row starting at `base`, in two steps so that the loads of several rows can be in flight
-    // together (col[] -> S4[] is a dependent chain of two ~1 us global loads; a warp that walks its rows one at a time
-    // spends its life waiting): fetch = every lane loads one neighbour's scalars; consume = the lanes park them in the
-    // warp's staging slot and all walk the slot (one broadcast 16-byte shared load per neighbour), recomputing their two
-    // features of x1_j.  The row is sorted, so the j < i neighbours are a prefix: no per-edge compare.
-    struct Fetch { int j; float4 s; int n; };
-    auto fetch = [&](int base, int ee) {
-      Fetch f;
-      const int e = base + lane;
-      f.j = 0x7fffffff;
-      f.s = make_float4(0.f, 0.f, 0.f, 0.f);
-      f.n = max(0, min(32, ee - base));
-      if (e < ee) {
-        f.j = col[e];
-        f.s = S4[(size_t)f.j * Q + q];
-      }
-      return f;
-    };
-    auto consume = [&](const Fetch& f, int i, float2& lt, float2& gt) {
-      float4* slot = s_hubp + warp * 32;
-      slot[lane] = f.s;
-      const int n = f.n;
-      const int nlt = __popc(__ballot_sync(FULL_MASK, f.j < i));
-      __syncwarp();
-      float2 a0 = make_float2(0.f, 0.f), a1 = a0;
-      int k = 0;
-      for (; k + 1 < nlt; k += 2) {
-        const float2 v0 = x1_of(slot[k]), v1 = x1_of(slot[k + 1]);
-        a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
-      }
-      if (k < nlt) { const float2 v = x1_of(slot[k]); a0.x += v.x; a0.y += v.y; }
-      lt.x += a0.x + a1.x; lt.y += a0.y + a1.y;
-      a0 = make_float2(0.f, 0.f); a1 = a0;
-      for (k = nlt; k + 1 < n; k += 2) {
-        const float2 v0 = x1_of(slot[k]), v1 = x1_of(slot[k + 1]);
-        a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
-      }
-      if (k < n) { const float2 v = x1_of(slot[k]); a0.x += v.x; a0.y += v.y; }
-      gt.x += a0.x + a1.x; gt.y += a0.y + a1.y;
-      __syncwarp();
-    };
-    auto store_u = [&](int r, float2 u) {
-      const uint32_t off = tc05::sw128_offset(r, 2 * lane);
-      const __nv_bfloat162 h = __floats2bfloat162_rn(u.x, u.y);
-      const float2 f = __bfloat1622float2(h);
-      const __nv_bfloat162 l = __floats2bfloat162_rn(u.x - f.x, u.y - f.y);
-      *reinterpret_cast<__nv_bfloat162*>(sA0 + off) = h;
-      *reinterpret_cast<__nv_bfloat162*>(sA0 + TR * 128 + off) = l;
-    };
-
-    // ---- gather: x1_i and u_i = g1 * sum_{j<i} x1_j + (1-g1) * sum_{j>i} x1_j, written as bf16 hi/lo A rows ----
-    // one warp per row; hub rows (power-law targets: a 2000-neighbour row would stall its warp while 15 others wait at
-    // the barrier) are deferred and gathered by all warps together below
-    constexpr int GR = 4;  // rows whose loads are in flight together
-#pragma unroll 1
-    for (int r0 = warp; r0 < TR; r0 += NW * GR) {
-      int eb[GR], ee[GR];
-      bool hub[GR];
-      Fetch f[GR];
-#pragma unroll
-      for (int k = 0; k < GR; ++k) {
-        const int i = i0 + r0 + NW * k;
-        eb[k] = ee[k] = 0;
-        if (i < node_end) { eb[k] = rowptr[i]; ee[k] = rowptr[i + 1]; }
-      }
-#pragma unroll
-      for (int k = 0; k < GR; ++k) {
-        hub[k] = ee[k] - eb[k] > HUB_DEG;
-        if (hub[k]) {
-          if (lane == 0) s_hubs[atomicAdd(s_nhub, 1)] = (uint8_t)(r0 + NW * k);
-          ee[k] = eb[k];
-        }
-        f[k] = fetch(eb[k], ee[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < GR; ++k) {
-        const int r = r0 + NW * k, i = i0 + r;
-        float2 u = make_float2(0.f, 0.f), x1 = u;
-        float c = 0.f, d1 = 0.f;
-        if (i < node_end) {
-          const float4 own = S4[(size_t)i * Q + q];
-          x1 = x1_of(own);
-          c = own.z;
-          d1 = own.w;
-          float2 lt = make_float2(0.f, 0.f), gt = lt;
-          consume(f[k], i, lt, gt);
-          for (int base = eb[k] + 32; base < ee[k]; base += 32) consume(fetch(base, ee[k]), i, lt, gt);
-          u.x = g1 * lt.x + (1.f - g1) * gt.x;
-          u.y = g1 * lt.y + (1.f - g1) * gt.y;
-        }
-        const uint32_t off = tc05::sw128_offset(r, 2 * lane);
-        if (!hub[k]) store_u(r, u);
-        {
-          const __nv_bfloat162 h = __floats2bfloat162_rn(x1.x, x1.y);
-          const float2 fl = __bfloat1622float2(h);
-          const __nv_bfloat162 l = __floats2bfloat162_rn(x1.x - fl.x, x1.y - fl.y);
-          *reinterpret_cast<__nv_bfloat162*>(sA1 + off) = h;
-          *reinterpret_cast<__nv_bfloat162*>(sA1 + TR * 128 + off) = l;
-        }
-        if (lane == 0) {
-          s_c[r] = c;
-          s_d1[r] = d1;
-        }
-      }
-    }
-    __syncthreads();
-    lap(GPH_GATHER);
-    for (int h = 0, nh = *s_nhub; h < nh; ++h) {  // hub rows: 32-edge chunks dealt over all warps, partials summed in warp order
-      const int r = s_hubs[h], i = i0 + r;
-      const int eb = rowptr[i], ee = rowptr[i + 1];
-      float2 lt = make_float2(0.f, 0.f), gt = lt;
-      for (int base = eb + 32 * warp; base < ee; base += 32 * NW * GR) {
-        Fetch f[GR];
-#pragma unroll
-        for (int k = 0; k < GR; ++k) f[k] = fetch(base + 32 * NW * k, ee);
-#pragma unroll
-        for (int k = 0; k < GR; ++k) consume(f[k], i, lt, gt);
-      }
-      s_hubp[warp * 32 + lane] = make_float4(lt.x, lt.y, gt.x, gt.y);  // (consume ends with a __syncwarp: the slot is free)
-      __syncthreads();
-      if (warp == 0) {
-        float4 t = s_hubp[lane];
-        for (int w = 1; w < NW; ++w) {
-          const float4 o = s_hubp[w * 32 + lane];
-          t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
-        }
-        store_u(r, make_float2(g1 * t.x + (1.f - g1) * t.z, g1 * t.y + (1.f - g1) * t.w));
-      }
-      __syncthreads();
-    }
-    tc05::fence_proxy_async_smem();
-    __syncthreads();
-    lap(GPH_HUBS);
+    // the tile's operands (bulk copies issued one tile ahead); every thread observes the completion itself, so the
+    // copied c / d1 words are visible to it
+    if (!tc05::mbar_wait(&bars[2], lphase)) __trap();
+    const float c = s_c[row], d1 = s_d1[row];
+    __syncthreads();  // c / d1 are in registers everywhere: their block may be overwritten by the next tile's copy
+    lap(GPH_LOAD);
 
     // ---- x2 = relu([u | x1] . Wx2 + d1mix * v1 + b_up1)  (gnn_model.py:341-348 for layer 1) ----
     if (tid == ISSUER) {
@@ -621,14 +660,13 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
         if (!tc05::mbar_wait(&bars[0], 0)) __trap();
         weights_ready = true;
       }
+      if (!tc05::mbar_wait(&bars[3], lphase)) __trap();
       tc05::fence_after_sync();
       issue(0, idesc64, sA0, sB + IMG_W1, F * 128, sA1, sB + IMG_W1 + 2 * F * 128, F * 128);
     }
+    lphase ^= 1;
     wait_mma();
-    {
-      const float d1 = s_d1[row];
-      epilogue64(0, sA0, [&](float a, int n) { return fmaxf(a + d1 * sV1[n] + sBup1[n], 0.f); });  // x2 replaces u
-    }
+    epilogue64(0, sA0, [&](float a, int n) { return fmaxf(a + d1 * sV1[n] + sBup1[n], 0.f); });  // x2 replaces u
     lap(GPH_X2);
     // ---- y1 = leaky_0.1([x1 | x2] . Wy1 + eta_q + c_i * theta)   (post_mp[0..2], x0 part folded into eta / theta) ----
     if (tid == ISSUER) {
@@ -636,13 +674,10 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
       issue(64, idesc64, sA1, sB + IMG_W2, F * 128, sA0, sB + IMG_W2 + 2 * F * 128, F * 128);
     }
     wait_mma();
-    {
-      const float c = s_c[row];
-      epilogue64(64, sA0, [&](float a, int n) {
-        const float o = a + sEta[n] + c * sTheta[n];
-        return o > 0.f ? o : 0.1f * o;
-      });  // y1 replaces x2
-    }
+    epilogue64(64, sA0, [&](float a, int n) {
+      const float o = a + sEta[n] + c * sTheta[n];
+      return o > 0.f ? o : 0.1f * o;
+    });  // y1 replaces x2
     lap(GPH_Y1);
     // ---- y2 = relu(y1 . P1 + b1) ----
     if (tid == ISSUER) {
@@ -650,6 +685,7 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
       issue(128, idesc64, sA0, sB + IMG_P1, F * 128, nullptr, nullptr, 0);
     }
     wait_mma();
+    if (tid == ISSUER && tn < num_tiles) load_u(tn);  // the u slot is dead: fetch the next tile's under the epilogues below
     epilogue64(128, sA1, [&](float a, int n) { return fmaxf(a + sB1[n], 0.f); });  // y2 replaces x1
     lap(GPH_Y2);
     // ---- y4 = relu(y2 . P2 + b2) . p3 + b3: one N = 256 GEMM, the 256-wide y3 only ever exists in TMEM ----
@@ -658,6 +694,7 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
       issue(256, idesc256, sA1, sB + IMG_P2, 4 * F * 128, nullptr, nullptr, 0);
     }
     wait_mma();
+    if (tid == ISSUER && tn < num_tiles) load_x1(tn);
     {
       float part = 0.f;
 #pragma unroll
@@ -674,9 +711,9 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
     }
     tc05::fence_before_sync();
     __syncthreads();
-    if (tid < TR && i0 + tid < node_end)  // neigh_pred + gossip_pred (lightning_model.py:625)
-      out[(size_t)(i0 + tid) * Q + q] =
-          s_c[tid] + ((s_part[tid] + s_part[TR + tid]) + (s_part[2 * TR + tid] + s_part[3 * TR + tid])) + b3;
+    if (cg == 0 && i0 + row < node_end)  // neigh_pred + gossip_pred (lightning_model.py:625)
+      out[(size_t)(i0 + row) * Q + q] =
+          c + ((s_part[row] + s_part[TR + row]) + (s_part[2 * TR + row] + s_part[3 * TR + row])) + b3;
     lap(GPH_Y4);
   }
   if (tid == ISSUER && !weights_ready) tc05::mbar_wait(&bars[0], 0);  // never exit with a bulk copy in flight
@@ -684,6 +721,9 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_layer1_tc_kernel(
   __syncthreads();
   if (warp == 0) tc05::tmem_dealloc(tmem, 512);
 }
+
+// tiles staged per launch pair (bounds the staging buffer: 8192 tiles = 545 MB)
+constexpr long long CHUNK_TILES = 8192;
 }  // namespace gtc
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -695,8 +735,16 @@ extern "C" {
 int64_t desco_gossip_weight_floats(void) { return WG_TOTAL; }
 int64_t desco_gossip_query_weight_floats(void) { return WQ_TOTAL; }
 
+int64_t desco_gossip_layer1_workspace_bytes(int32_t num_nodes, int32_t num_queries, int32_t precision) {
+  if (precision != DESCO_PRECISION_BF16X3 || num_nodes <= 0 || num_queries <= 0) return 0;
+  long long tiles = (((long long)num_nodes + gtc::TR - 1) / gtc::TR) * num_queries;
+  if (tiles > gtc::CHUNK_TILES) tiles = gtc::CHUNK_TILES;
+  return (int64_t)align_up((size_t)tiles * gtc::TILE_BYTES);
+}
+
 int64_t desco_gossip_workspace_bytes(int32_t num_nodes, int32_t num_queries) {
-  return (int64_t)(align_up((size_t)num_queries * QV * 4) + align_up((size_t)num_nodes * num_queries * sizeof(float4)));
+  return (int64_t)(align_up((size_t)num_queries * QV * 4) + align_up((size_t)num_nodes * num_queries * sizeof(float4))) +
+         desco_gossip_layer1_workspace_bytes(num_nodes, num_queries, DESCO_PRECISION_BF16X3);
 }
 
 int desco_gossip_tc_phase_cycles(uint64_t* out, int32_t reset) {
@@ -737,25 +785,33 @@ int desco_gossip_layer0(const int32_t* rowptr, const int32_t* col, int32_t node_
 
 int desco_gossip_layer1(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end, const float* s4,
                         int32_t num_queries, const float* qvec, const float* w_gossip, float* out, int32_t precision,
-                        void* stream) {
+                        void* workspace, int64_t workspace_bytes, void* stream) {
   if (node_begin < 0 || node_end < node_begin || num_queries < 0) return DESCO_EINVAL;
   if (precision != DESCO_PRECISION_FP32 && precision != DESCO_PRECISION_BF16X3) return DESCO_EINVAL;
   if (node_end == node_begin || num_queries == 0) return DESCO_OK;
   if (!rowptr || !col || !s4 || !qvec || !w_gossip || !out) return DESCO_EINVAL;
   if (precision == DESCO_PRECISION_BF16X3) {
+    if (!workspace) return DESCO_EINVAL;
+    const long long tc_tiles = (((long long)(node_end - node_begin) + gtc::TR - 1) / gtc::TR) * num_queries;
+    const long long cap = workspace_bytes / gtc::TILE_BYTES;  // tiles the staging buffer holds
+    if (cap < 1) return DESCO_ENOMEM;
     static bool tc_attr_set = false;
     if (!tc_attr_set) {
-      DESCO_CUDA_TRY(cudaFuncSetAttribute(gtc::gossip_layer1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      DESCO_CUDA_TRY(cudaFuncSetAttribute(gtc::gossip_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           gtc::SMEM_BYTES));
       tc_attr_set = true;
     }
-    const long long tc_tiles = (((long long)(node_end - node_begin) + gtc::TR - 1) / gtc::TR) * num_queries;
     const int sms = desco_num_sms();
-    const unsigned grid = (unsigned)(tc_tiles < sms ? tc_tiles : sms);
-    DescoProfScope prof(DESCO_PROF_GOSSIP_L1, (cudaStream_t)stream);
-    gtc::gossip_layer1_tc_kernel<<<grid, gtc::THREADS_TC, gtc::SMEM_BYTES, (cudaStream_t)stream>>>(
-        rowptr, col, node_begin, node_end, reinterpret_cast<const float4*>(s4), num_queries, qvec, w_gossip, out);
-    DESCO_LAUNCH_CHECK();
+    for (long long t0 = 0; t0 < tc_tiles; t0 += cap) {
+      const int n = (int)(tc_tiles - t0 < cap ? tc_tiles - t0 : cap);
+      DescoProfScope prof(DESCO_PROF_GOSSIP_L1, (cudaStream_t)stream, 2);
+      gtc::gossip_gather_kernel<<<n, gtc::G_THREADS, 0, (cudaStream_t)stream>>>(
+          rowptr, col, node_begin, node_end, reinterpret_cast<const float4*>(s4), num_queries, qvec, w_gossip, t0,
+          (uint8_t*)workspace);
+      gtc::gossip_chain_kernel<<<n < sms ? n : sms, gtc::THREADS_TC, gtc::SMEM_BYTES, (cudaStream_t)stream>>>(
+          node_begin, node_end, num_queries, qvec, w_gossip, t0, n, (const uint8_t*)workspace, out);
+      DESCO_LAUNCH_CHECK();
+    }
     return DESCO_OK;
   }
   const size_t smem = (size_t)(TM * LDX + 2 * F * F + 2 * TM) * sizeof(float);
@@ -783,10 +839,13 @@ int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_
   if (!workspace || workspace_bytes < desco_gossip_workspace_bytes(num_nodes, num_queries)) return DESCO_ENOMEM;
   float* qvec = (float*)workspace;
   float* s4 = (float*)((char*)workspace + align_up((size_t)num_queries * QV * 4));
+  char* stage = (char*)s4 + align_up((size_t)num_nodes * num_queries * sizeof(float4));
+  const int64_t stage_bytes = workspace_bytes - (int64_t)(stage - (char*)workspace);
   int rc;
   if ((rc = desco_gossip_prepare_queries(query_emb, num_queries, w_gossip_query, qvec, out_gates, stream))) return rc;
   if ((rc = desco_gossip_layer0(rowptr, col, 0, num_nodes, x, num_queries, qvec, s4, stream))) return rc;
-  return desco_gossip_layer1(rowptr, col, 0, num_nodes, s4, num_queries, qvec, w_gossip, out, precision, stream);
+  return desco_gossip_layer1(rowptr, col, 0, num_nodes, s4, num_queries, qvec, w_gossip, out, precision, stage, stage_bytes,
+                             stream);
 }
 
 }  // extern "C"

@@ -402,8 +402,11 @@ def _gossip_forward_node_range(self, rowptr, col, x, query_emb, node_begin, node
         s4 = exchange(s4_full_local[node_begin:node_end].contiguous()).contiguous()  # halo exchange -> s4[N,Q,4] everywhere
         out_full = torch.zeros((N, Q), dtype=torch.float32, device=dev)
         if n_loc:
+            sb = int(lib.desco_gossip_layer1_workspace_bytes(n_loc, Q, PRECISION[self.precision]))
+            stage = torch.empty(max(sb, 1), dtype=torch.uint8, device=dev)
             _lib.check(lib.desco_gossip_layer1(_ptr(rowptr), _ptr(col), node_begin, node_end, _ptr(s4), Q, _ptr(qvec),
-                                               _ptr(w["wg"]), _ptr(out_full), PRECISION[self.precision], st), "gossip_layer1")
+                                               _ptr(w["wg"]), _ptr(out_full), PRECISION[self.precision], _ptr(stage), sb, st),
+                       "gossip_layer1")
     return exchange(out_full[node_begin:node_end].contiguous())
 
 

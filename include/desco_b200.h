@@ -205,8 +205,8 @@ int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const f
  * the counts of its halo have been exchanged:  prepare_queries -> layer0 (any node range; needs x of the
  * neighbours) -> layer1 (needs s4 of the neighbours).  qvec: [Q, 256] floats, s4: [N, Q, 4] floats.
  * ---------------------------------------------------------------------------------------------------------------- */
-/* Profiling aid: clock64 cycles thread 0 of every CTA of the tensor-core layer-1 kernel spent per phase since the last
- * reset (out[6]: gather, hub rows, x2, y1, y2, y4 GEMM + epilogue). */
+/* Profiling aid: clock64 cycles thread 0 of every CTA of the tensor-core chain kernel (gossip_chain_kernel) spent per phase since the last
+ * reset (out[6]: operand wait, x2, y1, y2, y4 GEMM + epilogue, spare). */
 int desco_gossip_tc_phase_cycles(uint64_t* out, int32_t reset);
 int64_t desco_gossip_weight_floats(void);
 int64_t desco_gossip_query_weight_floats(void);
@@ -217,7 +217,11 @@ int desco_gossip_layer0(const int32_t* rowptr, const int32_t* col, int32_t node_
                         int32_t num_queries, const float* qvec, float* s4, void* stream);
 int desco_gossip_layer1(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end, const float* s4,
                         int32_t num_queries, const float* qvec, const float* w_gossip, float* out, int32_t precision,
-                        void* stream);
+                        void* workspace, int64_t workspace_bytes, void* stream);
+/* Staging bytes desco_gossip_layer1 wants for a range of num_nodes nodes (0 for DESCO_PRECISION_FP32; for
+ * DESCO_PRECISION_BF16X3 the operand images of up to 8192 tiles of 128 nodes x 1 query, 65 KB each - any multiple of one
+ * tile works, the range is walked in chunks). */
+int64_t desco_gossip_layer1_workspace_bytes(int32_t num_nodes, int32_t num_queries, int32_t precision);
 int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_nodes, const float* x,
                          int32_t num_queries, const float* query_emb, const float* w_gossip,
                          const float* w_gossip_query, float* out, float* out_gates, void* workspace,

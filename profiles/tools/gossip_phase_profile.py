@@ -27,5 +27,5 @@ b.record(); torch.cuda.synchronize()
 lib.desco_gossip_tc_phase_cycles(out, 1)
 tot = float(sum(out))
 print("forward ms", a.elapsed_time(b), "cycles per CTA", tot / 148)
-for n, v in zip(("gather", "hubs", "x2", "y1", "y2", "y4"), out):
+for n, v in zip(("load", "x2", "y1", "y2", "y4", "spare"), out):
     print(f"{n:8s} {v / 148:12.0f} cyc/CTA  {v / tot:.3f}")
