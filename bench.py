@@ -44,6 +44,16 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        for k in ("bf16_tflops_sustained", "bf16_tflops"):  # the chain is timed inside a long forward: sustained figure
+            if k in d:
+                return float(d[k]), f"measured (MEASURED_PEAKS.json {k})"
+    return 1590.0, "fallback (B200_PROFILING.md)"
+
+
 def build_workload(seed: int):
     from desco_b200.graph import first_nonempty_centres, gen_enzymes_shaped
 
@@ -188,24 +198,42 @@ def run_gossip_leg(args, dev, rank, world, lib, model, timed):
 
     steps = max(3, min(args.steps, 10))
     ms, launches, prof = timed(step, steps, 3, profile=True)
+    # tensor-core share: the chain kernel's own clock64 phase counters over one more (untimed) forward
+    import ctypes
+
+    cyc = (ctypes.c_uint64 * 6)()
+    lib.desco_gossip_tc_phase_cycles(cyc, 1)
+    step()
+    torch.cuda.synchronize()
+    lib.desco_gossip_tc_phase_cycles(cyc, 1)
     if rank != 0:
         return None
     peak, peak_src = _peaks()
-    l1_ms = prof[0][4] / max(prof[1][4], 1)
-    l0_ms = prof[0][3] / max(prof[1][3], 1)
+    sm_hz = 1e6 * float(torch.cuda.get_device_properties(dev).clock_rate) / 1e3  # kHz -> Hz (max SM clock)
+    chain_ms = 1e3 * (sum(cyc) / torch.cuda.get_device_properties(dev).multi_processor_count) / sm_hz
+    mm_flops = 2.0 * (128 * 64 + 128 * 64 + 64 * 64 + 64 * 256) * N * Q  # the four GEMMs of the chain, per (node, query)
+    tpeak, tsrc = _tensor_peak()
+    l1_ms = prof[0][4] / steps  # per step: layer 1 is a gather + chain launch pair per chunk of 8192 tiles
+    l0_ms = prof[0][3] / steps
     alg = Q * (512 * M + 1280 * N) + 8 * Q * N + 8 * M  # reference formulation, fp32 [.,64] rows
     return {
         "metric": "gossip_target_nodes_per_sec", "value": world * N * steps / (ms * 1e-3), "unit": "target-nodes/s",
         "ms_per_step": ms / steps, "steps": steps,
         "workload": f"powerlaw_chunglu_{N}nodes_{M // 2}undirected_edges_x{Q}queries_per_gpu", "nodes": N,
         "directed_edges": M, "queries": Q, "gpu_launches": int(launches),
-        "stage_ms": {"layer0_scalar_sweep": l0_ms, "layer1_recompute_gather_postmp": l1_ms},
+        "stage_ms": {"layer0_scalar_sweep": l0_ms, "layer1_recompute_gather_plus_tcgen05_chain": l1_ms},
+        "precision": "bf16x3 tcgen05 GEMM chain, fp32 accumulate (1e-4 parity path)",
         "roofline": {"kernel": "gossip layer0 + layer1 kernels (whole forward)", "bound": "hbm",
                      "achieved": alg / ((l0_ms + l1_ms) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / ((l0_ms + l1_ms) * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": alg,
                      "peak_source": peak_src,
+                     "tensor": {"kernel": "gossip_chain_kernel", "bound": "tensor", "unit": "TFLOP/s",
+                                "achieved": 3 * mm_flops / (chain_ms * 1e-3) / 1e12, "peak": tpeak, "peak_source": tsrc,
+                                "frac": 3 * mm_flops / (chain_ms * 1e-3) / 1e12 / tpeak, "chain_ms_per_step": chain_ms,
+                                "note": "bf16 tensor flops issued = 3 passes (hi.hi + lo.hi + hi.lo) x the fp32-equivalent "
+                                        "flops of the four GEMMs; time = the chain kernel's per-CTA clock64 total at the max SM clock"},
                      "note": "algorithmic bytes are the reference formulation's (64-wide fp32 rows per edge and query); "
-                             "the kernels move 16 B per edge and query instead, so the fraction can exceed 1"},
+                             "the kernels move 16 B per edge and query and recompute the rows instead, so the fraction can exceed 1"},
     }
 
 

@@ -320,9 +320,9 @@ constexpr int HUB_DEG = 512;                     // rows with more neighbours ar
 // ---------------------------------------------------------------- gather ----------------------------------------
 constexpr int G_THREADS = 256;
 constexpr int G_NW = G_THREADS / 32;
-constexpr int GR = 2;  // rows whose loads are in flight together (more = more code: the kernel is I-cache sensitive)
+constexpr int GR = 1;  // rows whose loads are in flight together (more = more code: the kernel is I-cache sensitive)
 
-__global__ void __launch_bounds__(G_THREADS, 3) gossip_gather_kernel(
+__global__ void __launch_bounds__(G_THREADS, 5) gossip_gather_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int node_begin, int node_end,
     const float4* __restrict__ S4, int Q, const float* __restrict__ qvec, const float* __restrict__ wg, long long tile0,
     uint8_t* __restrict__ stage) {
