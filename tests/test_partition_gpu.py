@@ -203,3 +203,42 @@ def test_large_path_equals_bitset_path_full_sweep(cuda_device):
     b = _gpu_partition(csr, 2, "hetero", large=True)
     for k in KEYS:
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_one_call_partition_grows_its_buffers(cuda_device):
+    """desco_partition_batch reports ENOBUFS with the exact sizes when the caller's capacity is too small; the Python
+    wrapper re-allocates once and the result is still bit-exact (here the capacity estimate is forced down to 1 row per
+    centre and 1 edge per row on a dense IMDB-shaped set)."""
+    from oracle import partition as P
+
+    from desco_b200 import data as D
+
+    csr = gen_imdb_shaped(seed=4, num_graphs=12)
+    ref = P.partition_dataset(csr, 4, mode="hetero")
+    saved = dict(D._CAPACITY)
+    try:
+        D._CAPACITY.update(rows_per_centre=0.5, edges_per_row=0.5)
+        b = _gpu_partition(csr, 4, "hetero", large=False)
+        assert D._CAPACITY["rows_per_centre"] > 1.0  # learnt from the retry
+    finally:
+        D._CAPACITY.update(saved)
+    for k in KEYS:
+        assert np.array_equal(b[k], ref[k]), k
+
+
+def test_one_call_partition_empty_and_edge_free(cuda_device):
+    """No centres at all, and centres whose neighborhoods are all edge-free (dropped, workload.py:253-256)."""
+    import networkx as nx
+
+    from desco_b200.graph import csr_from_networkx
+
+    g = nx.Graph()
+    g.add_nodes_from(range(4))
+    g.add_edge(2, 3)
+    csr = csr_from_networkx([g])
+    b = _gpu_partition(csr, 4, "hetero", centres=np.zeros(0, dtype=np.int32), large=False)
+    assert len(b["centre"]) == 0 and b["nbh_ptr"].tolist() == [0] and len(b["edge_col"]) == 0
+    b = _gpu_partition(csr, 4, "hetero", centres=np.array([0, 1, 2], dtype=np.int32), large=False)
+    assert len(b["centre"]) == 0 and b["indicator"].tolist() == [False, False, False]
+    b = _gpu_partition(csr, 4, "hetero", large=False)
+    assert b["centre"].tolist() == [3] and b["node_gid"].tolist() == [2, 3] and b["indicator"].tolist() == [False, False, False, True]
