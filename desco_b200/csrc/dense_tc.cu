@@ -138,13 +138,14 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
   {
     const int q = warp & 3, half = warp >> 2;
     const int r = m0 + 32 * q + lane;
-    const int cols_per_half = p.nblk / 2;
-    for (int c = half * cols_per_half; c < (half + 1) * cols_per_half; c += 16) {
+    const int cols_per_half = (p.nblk + 31) / 32 * 16;  // whole 16-column loads; the tail of the second half is masked
+    for (int c = half * cols_per_half; c < (half + 1) * cols_per_half && c < p.nblk; c += 16) {
       float v[16];
       tc05::tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + c, v);
       if (r < p.M) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
+          if (c + i >= p.nblk) break;
           float o[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
           if (p.bias) {
             const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + c + i);
@@ -176,7 +177,7 @@ int desco_internal_dense_tc(const float* X, int ldx, const void* Wimg, const flo
                             int ldy, int M, int K, int N, int nblk, int act, float slope, int passes, int32_t* status,
                             cudaStream_t s) {
   if (M == 0) return DESCO_OK;
-  if (K % 64 || nblk % 32 || nblk > 128 || N % nblk || passes < 1 || passes > 6 || !status) return DESCO_EINVAL;
+  if (K % 64 || nblk % 16 || nblk > 160 || N % nblk || passes < 1 || passes > 6 || !status) return DESCO_EINVAL;
   const size_t smem = 1024 + 2 * (size_t)(3 * A_BYTES + 3 * nblk * 128) + 64;
   static size_t attr = 0;
   if (smem > attr) {

@@ -500,14 +500,13 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
   const float* z = ws.pool;
   if (fused) {  // the same chain on the tensor pipe (csrc/dense_tc.cu); images in w_readout_tc, biases from w_readout
     const int passes = precision == DESCO_PRECISION_BF16X3 ? 6 : 1;  // the readout sums cancel heavily: full 3-way split
-    const uint8_t* img = (const uint8_t*)w_readout_tc;
-    const uint8_t* iWanc = img; img += (size_t)emb_ld * emb_ld * 6;   // bf16 hi + mid + lo = 6 bytes per weight
-    const uint8_t* iP0 = img; img += (size_t)emb_ld * F * 6;
-    const uint8_t* iP1 = img; img += (size_t)F * F * 6;
-    const uint8_t* iP2 = img; img += (size_t)F * 4 * F * 6;
-    const uint8_t* iP3 = img;
-    if (emb_ld % 96) return DESCO_EINVAL;
-    if ((rc = desco_internal_dense_tc(ws.emb_a, emb_ld, iWanc, banc, ws.pool, emb_ld, ws.z, emb_ld, G, emb_ld, emb_ld, 96, 2, 0.1f, passes, status, s))) return rc;
+    // bf16 hi + mid + lo = 6 bytes per weight; the blob starts with the anchor_mlp images (the post_mp images that follow
+    // are for a dense_tc post_mp chain; the default chain below is the single-launch fp32 kernel)
+    const uint8_t* iWanc = (const uint8_t*)w_readout_tc;
+    // 144-column blocks: 576 / 144 = 4 column blocks x 32 row blocks = 128 CTAs for 4096 neighborhoods, one wave on 148 SMs
+    // (96-column blocks were 192 CTAs = two waves)
+    if (emb_ld % 144) return DESCO_EINVAL;
+    if ((rc = desco_internal_dense_tc(ws.emb_a, emb_ld, iWanc, banc, ws.pool, emb_ld, ws.z, emb_ld, G, emb_ld, emb_ld, 144, 2, 0.1f, passes, status, s))) return rc;
     return desco_internal_readout_chain(ws.z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, s);
   }
   if (hetero) {  // z = pool_count + LeakyReLU_0.1(anchor(emb_canonical))  (gnn_model.py:69-73, 88-89, 107)

@@ -40,7 +40,6 @@ constexpr int CINP = NB + 8;            // row pitch (bf16) of the canonical-inp
 
 // per-layer weight blob (bytes)
 constexpr int OFF_BHI = 0;
-constexpr int OFF_BLO = NB * 128;
 constexpr int OFF_BIASC = 2 * NB * 128;
 constexpr int OFF_BIASA = OFF_BIASC + F * 4;
 // canonical-row weights as ready-made mma.sync B fragments (tcpack.pack_mma_b_frags): per (column tile of 8, k-step of

@@ -175,7 +175,7 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
     f32 = lambda parts: torch.cat(parts).to(torch.float32).to(dev).contiguous()
     out = {"pre": f32(pre), "layers": f32(layers), "readout": f32(ro)}
     if tc_layers:
-        out["readout_tc"] = torch.cat([pack_dense_tc(d(base.anchor_mlp[0].weight), 96), pack_dense_tc(d(base.post_mp[0].weight), 64),
+        out["readout_tc"] = torch.cat([pack_dense_tc(d(base.anchor_mlp[0].weight), 144), pack_dense_tc(d(base.post_mp[0].weight), 64),
                                        pack_dense_tc(d(base.post_mp[3].weight), 64), pack_dense_tc(d(base.post_mp[5].weight), 128),
                                        pack_dense_tc(d(base.post_mp[7].weight), 64)]).to(dev).contiguous()
         out["layers_tc"] = torch.cat(tc_layers).to(dev).contiguous()

@@ -159,10 +159,11 @@ int desco_shmp_edge_types(const int32_t* edge_ptr, const int32_t* edge_col, int3
  *   w_layers_tc  tensor-core form of w_layers for precision BF16X3 / BF16 (hetero batches only), per layer
  *             desco_shmp_tc_layer_bytes() bytes: the [tri | tride | self] weights as a 192 x 64 K-major operand, split in
  *             bf16 hi / lo and pre-swizzled (SWIZZLE_128B shared-memory images, desco_b200.tcpack), then fp32
- *             bias_c[64], bias_a[64], Wa^T[64][192], Cw^T[128][64].  May be NULL for precision FP32 (then w_layers is
+ *             bias_c[64], bias_a[64], then Wa [192][64] and Cw [64][128] as warp-level mma.sync B fragments (bf16 hi / lo,
+ *             desco_b200.tcpack.pack_mma_b_frags; same byte count as fp32).  May be NULL for precision FP32 (then w_layers is
  *             required); w_layers may be NULL for the tensor-core precisions.
  *   w_readout_tc  tensor-core form of the readout weights (biases still come from w_readout): operand images of Wanc
- *             (6 column blocks of 96), P0, P1, P2 (2 blocks of 128), P3 in that order, each
+ *             (4 column blocks of 144), P0, P1, P2 (2 blocks of 128), P3 in that order, each
  *             [column block][64-wide K atom][hi | mid | lo] (3-way bf16 split, 6 tensor-core passes = fp32-grade
  *             products) as built by desco_b200.tcpack.pack_dense_tc.
  * out_emb: [num_neighborhoods, 64].  precision: DESCO_PRECISION_*.
