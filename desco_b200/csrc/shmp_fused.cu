@@ -479,15 +479,17 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         {
           const int q = warp & 3, cg = warp >> 2;  // TMEM lane quarter of this warp, column group of 48
           const int r = 32 * q + lane;
+          uint32_t v[3][16];  // the three loads of this warp's 48 columns are in flight together
+#pragma unroll
+          for (int j = 0; j < 3; ++j) tc05::tmem_ld16_async(tmem + (static_cast<uint32_t>(32 * q) << 16) + cg * 48 + j * 16, v[j]);
+          tc05::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             const int c0 = cg * 48 + j * 16;
-            float v[16];
-            tc05::tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + c0, v);
             if (r < R) {
               float* dst = (c0 < 2 * F) ? (sP + r * LDP + c0) : (sStage + r * LDS_ + (c0 - 2 * F));
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4*>(dst + i) = make_uint4(v[j][i], v[j][i + 1], v[j][i + 2], v[j][i + 3]);
             }
           }
         }
