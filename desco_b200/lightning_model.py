@@ -74,6 +74,21 @@ def pack_head_weights_tc(count_model: nn.Sequential, hidden: int) -> torch.Tenso
     return torch.cat([pack_dense_tc(W1[:, :hidden], 128), pack_dense_tc(W1[:, hidden:], 128)]).to(count_model[0].weight.device)
 
 
+
+def _load_lightning_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **override):
+    """``pl.LightningModule.load_from_checkpoint`` for the reference's ``.ckpt`` files (``main.py:216-233,319-334``): a
+    pickled dict with ``state_dict`` (keys as produced by ``to_hetero_old``, SURVEY App. B.3 - the modules here use the
+    same names) and ``hyper_parameters`` (the constructor arguments saved by ``save_hyperparameters()``)."""
+    ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+    hp = dict(ckpt.get("hyper_parameters", {}))
+    hp.update(override)
+    model = cls(hp.pop("input_dim", 1), hp.pop("hidden_dim", 64), hp.pop("args", None), **hp)
+    if hasattr(model, "on_load_checkpoint"):
+        model.on_load_checkpoint(ckpt)
+    model.load_state_dict(ckpt["state_dict"], strict=strict)
+    return model
+
+
 class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
     def __init__(self, input_dim=1, hidden_dim=64, args=None, **kwargs):
         super().__init__()
@@ -104,6 +119,8 @@ class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
         a = checkpoint["hyper_parameters"]["args"]
         if not (a.use_hetero and a.use_tconv and getattr(a, "use_canonical", True)):
             raise NotImplementedError("checkpoint was trained without hetero/tconv/canonical: not a CUDA path")
+
+    load_from_checkpoint = classmethod(_load_lightning_checkpoint)
 
     # ---- precision / batching knobs ----
     def set_precision(self, precision: str):
@@ -227,6 +244,8 @@ class GossipCountingModel(nn.Module):
         self.kwargs = kwargs
         self.query_emb = None
         self.eval()
+
+    load_from_checkpoint = classmethod(_load_lightning_checkpoint)
 
     def set_query_emb(self, query_emb: torch.Tensor, query_ids=None, queries=None):
         self.query_emb = query_emb.detach()
