@@ -242,3 +242,25 @@ def test_one_call_partition_empty_and_edge_free(cuda_device):
     assert len(b["centre"]) == 0 and b["indicator"].tolist() == [False, False, False]
     b = _gpu_partition(csr, 4, "hetero", large=False)
     assert b["centre"].tolist() == [3] and b["node_gid"].tolist() == [2, 3] and b["indicator"].tolist() == [False, False, False, True]
+
+
+def test_large_path_hub_rows_equal_bitset_path(cuda_device):
+    """A power-law target with 1000-neighbour hubs: rows above 256 entries are walked by all warps of a shared-memory-tier
+    CTA together, and the depth-2 balls around hubs overflow into the team tier.  Both must equal the bitset kernel."""
+    from desco_b200.graph import gen_powerlaw
+
+    csr = gen_powerlaw(20000, 200000, seed=9, max_deg_frac=0.05)
+    deg = np.diff(csr.rowptr)
+    assert deg.max() > 512
+    rng = np.random.default_rng(2)
+    hubs = np.argsort(deg)[-24:]
+    centres = np.unique(np.concatenate([rng.choice(csr.num_nodes, size=1500, replace=False), hubs,
+                                        csr.col[csr.rowptr[hubs[-1]]:csr.rowptr[hubs[-1]] + 64]])).astype(np.int32)
+    a = _gpu_partition(csr, 2, "hetero", centres, large=False)
+    b = _gpu_partition(csr, 2, "hetero", centres, large=True)
+    for k in KEYS:
+        assert np.array_equal(a[k], b[k]), k
+    a = _gpu_partition(csr, 3, "canonical", centres[::7], large=False)
+    b = _gpu_partition(csr, 3, "canonical", centres[::7], large=True)
+    for k in KEYS:
+        assert np.array_equal(a[k], b[k]), k
