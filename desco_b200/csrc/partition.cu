@@ -630,6 +630,28 @@ constexpr uint32_t SP_FLAG = 0x80000000u;
 constexpr uint32_t SP_MASK = 0x7fffffffu;
 constexpr int SP_THREADS = 256;
 
+// Streams col[rb, re) of one adjacency row through a warp, 32 entries per call of f(v, valid), with PF independent
+// 128-byte loads in flight: every chunk of a cold row is its own ~1 us L2 / HBM access and the early exit of a sorted row
+// (f returns true, warp-uniformly) would otherwise make them a dependent chain.
+template <int PF, typename Fn>
+__device__ __forceinline__ void stream_row(const int32_t* __restrict__ col, int rb, int re, Fn f) {
+  const int lane = lane_id();
+  for (int e0 = rb; e0 < re; e0 += 32 * PF) {
+    int v[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+      const int e = e0 + 32 * k + lane;
+      v[k] = (e < re) ? col[e] : 0x7fffffff;
+    }
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+      if (e0 + 32 * k >= re) return;
+      if (f(v[k], e0 + 32 * k + lane < re)) return;
+    }
+  }
+}
+constexpr int ROW_PF = 4;
+
 struct SparseArgs {
   const int32_t* rowptr; const int32_t* col; const int32_t* graph_ptr; int num_graphs;
   const int32_t* centres; int num_centres, depth, mode;
@@ -737,13 +759,11 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
       for (int i = lb + warp; i < le; i += NW) {
         const int u = (int)set.L[i];
         const int rb = rowptr[u], re = rowptr[u + 1];
-        for (int e0 = rb; e0 < re; e0 += 32) {
-          const int e = e0 + lane;
-          const int v = (e < re) ? col[e] : 0x7fffffff;
-          const bool above = restricted && e < re && v > centre;
-          if (e < re && !above) set.insert(v);
-          if (__any_sync(FULL_MASK, above)) break;  // sorted row: nothing further passes
-        }
+        stream_row<ROW_PF>(col, rb, re, [&](int v, bool valid) {
+          const bool above = restricted && valid && v > centre;
+          if (valid && !above) set.insert(v);
+          return __any_sync(FULL_MASK, above) != 0;  // sorted row: nothing further passes
+        });
       }
       __syncthreads();
       lb = le;
@@ -769,10 +789,8 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
             const int u = (int)set.R[i];
             const int rb = rowptr[u], re = rowptr[u + 1];
             int cnt = 0;  // every member <= centre next to a reached node is reached too: this IS the induced degree
-            for (int e0 = rb; e0 < re; e0 += 32) {
-              const int e = e0 + lane;
-              const int v = (e < re) ? col[e] : 0x7fffffff;
-              if (e < re && v <= centre) {
+            stream_row<ROW_PF>(col, rb, re, [&](int v, bool valid) {
+              if (valid && v <= centre) {
                 const int s = set.find(v);
                 if (s >= 0) {
                   ++cnt;
@@ -785,8 +803,8 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
                   }
                 }
               }
-              if (__any_sync(FULL_MASK, e < re && v > centre)) break;
-            }
+              return __any_sync(FULL_MASK, valid && v > centre) != 0;
+            });
             cnt = warp_sum(cnt);
             if (lane == 0) {
               rank16[set.find(u)] = (uint16_t)min(cnt, 0xffff);  // parked beside the hash slot until the sort
@@ -871,12 +889,10 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
       const int u = (int)set.R[i];
       const int rb = rowptr[u], re = rowptr[u + 1];
       int cnt = 0;
-      for (int e0 = rb; e0 < re; e0 += 32) {
-        const int e = e0 + lane;
-        const int v = (e < re) ? col[e] : 0x7fffffff;
-        if (e < re && v <= limit && set.reached(v)) ++cnt;
-        if (__any_sync(FULL_MASK, e < re && v > limit)) break;
-      }
+      stream_row<ROW_PF>(col, rb, re, [&](int v, bool valid) {
+        if (valid && v <= limit && set.reached(v)) ++cnt;
+        return __any_sync(FULL_MASK, valid && v > limit) != 0;
+      });
       cnt = warp_sum(cnt);
       if (lane == 0) {
         if (p.fill) {
@@ -916,16 +932,14 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
         const int u = (int)set.R[i];
         const int rb = rowptr[u], re = rowptr[u + 1];
         int out = (i == 0) ? eo : p.edge_ptr[n0 + i];
-        for (int e0 = rb; e0 < re; e0 += 32) {
-          const int e = e0 + lane;
-          const int v = (e < re) ? col[e] : 0x7fffffff;
-          const int slot = (e < re && v <= limit) ? set.find(v) : -1;
+        stream_row<ROW_PF>(col, rb, re, [&](int v, bool valid) {
+          const int slot = (valid && v <= limit) ? set.find(v) : -1;
           const bool ok = slot >= 0 && (set.keys[slot] & SP_FLAG);
           const uint32_t m = __ballot_sync(FULL_MASK, ok);
           if (ok) p.edge_col[out + __popc(m & ((1u << lane) - 1u))] = n0 + (int)rank16[slot];
           out += __popc(m);
-          if (__any_sync(FULL_MASK, e < re && v > limit)) break;
-        }
+          return __any_sync(FULL_MASK, valid && v > limit) != 0;
+        });
       }
     }
     __syncthreads();
@@ -1027,13 +1041,11 @@ __device__ __forceinline__ void team_rows(const int32_t* __restrict__ rowptr, co
     for (int i = lb + gw; i < le; i += TW) {
       const int u = __ldcg(list + i);
       const int rb = rowptr[u], re = rowptr[u + 1];
-      for (int e0 = rb; e0 < re; e0 += 32) {
-        const int e = e0 + lane;
-        const int v = (e < re) ? col[e] : 0;
-        const bool ok = e < re && v <= limit;
+      stream_row<ROW_PF>(col, rb, re, [&](int v, bool valid) {
+        const bool ok = valid && v <= limit;
         f(v, ok);
-        if (!__all_sync(FULL_MASK, ok)) break;
-      }
+        return !__all_sync(FULL_MASK, ok);
+      });
     }
   } else {
     for (int i = lb; i < le; ++i) {
