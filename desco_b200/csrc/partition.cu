@@ -650,7 +650,7 @@ __device__ __forceinline__ void stream_row(const int32_t* __restrict__ col, int 
     }
   }
 }
-constexpr int ROW_PF = 4;
+constexpr int ROW_PF = 8;
 
 struct SparseArgs {
   const int32_t* rowptr; const int32_t* col; const int32_t* graph_ptr; int num_graphs;
