@@ -650,7 +650,7 @@ __device__ __forceinline__ void stream_row(const int32_t* __restrict__ col, int 
     }
   }
 }
-constexpr int ROW_PF = 8;
+constexpr int ROW_PF = 4;
 
 struct SparseArgs {
   const int32_t* rowptr; const int32_t* col; const int32_t* graph_ptr; int num_graphs;
@@ -1249,13 +1249,11 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
           const int u = __ldcg(p.node_gid + n0 + i);
           const int rb = rowptr[u], re = rowptr[u + 1];
           int cnt = 0;
-          for (int e0 = rb; e0 < re; e0 += 32) {
-            const int e = e0 + lane;
-            const int v = (e < re) ? col[e] : 0;
-            const bool ok = e < re && v <= limit;
+          stream_row<ROW_PF>(col, rb, re, [&](int v, bool valid) {
+            const bool ok = valid && v <= limit;
             if (ok) cnt += (__ldcg(&RP[(v - lo) >> 5].x) >> ((v - lo) & 31)) & 1u;
-            if (!__all_sync(FULL_MASK, ok)) break;
-          }
+            return !__all_sync(FULL_MASK, ok);
+          });
           cnt = warp_sum(cnt);
           if (lane == 0) p.edge_ptr[n0 + 1 + i] = cnt;
           wsum += cnt;
@@ -1286,10 +1284,8 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
           const int u = __ldcg(p.node_gid + n0 + i);
           const int rb = rowptr[u], re = rowptr[u + 1];
           int out = (i == 0) ? eo : __ldcg(p.edge_ptr + n0 + i);
-          for (int e0 = rb; e0 < re; e0 += 32) {
-            const int e = e0 + lane;
-            const int v = (e < re) ? col[e] : 0;
-            const bool ok = e < re && v <= limit;
+          stream_row<ROW_PF>(col, rb, re, [&](int v, bool valid) {
+            const bool ok = valid && v <= limit;
             uint2 rp = make_uint2(0u, 0u);
             if (ok) rp = __ldcg(&RP[(v - lo) >> 5]);
             const uint32_t bit = 1u << ((v - lo) & 31);
@@ -1297,8 +1293,8 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
             const uint32_t m = __ballot_sync(FULL_MASK, in);
             if (in) p.edge_col[out + __popc(m & ((1u << lane) - 1u))] = n0 + (int)rp.y + __popc(rp.x & (bit - 1u));
             out += __popc(m);
-            if (!__all_sync(FULL_MASK, ok)) break;
-          }
+            return !__all_sync(FULL_MASK, ok);
+          });
         }
         sn = team_sync(c, s_snap);  // every team-mate is done reading the reached words
       }
