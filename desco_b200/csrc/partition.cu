@@ -628,7 +628,7 @@ __global__ void edge_types_kernel(const int32_t* __restrict__ edge_ptr, const in
 constexpr uint32_t SP_EMPTY = 0xffffffffu;
 constexpr uint32_t SP_FLAG = 0x80000000u;
 constexpr uint32_t SP_MASK = 0x7fffffffu;
-constexpr int SP_THREADS = 256;
+constexpr int SP_THREADS = 1024;
 
 // Streams col[rb, re) of one adjacency row through a warp, 32 entries per call of f(v, valid), with PF independent
 // 128-byte loads in flight: every chunk of a cold row is its own ~1 us L2 / HBM access and the early exit of a sorted row

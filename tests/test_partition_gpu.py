@@ -155,8 +155,8 @@ def test_large_path_matches_reference_golden(cuda_device, golden_dir, name, mode
 
 @pytest.mark.parametrize("caps,label", [
     (DEFAULT_CAPS, "tier0"),
-    ((9, 16, 8, 12, 512, 256), "tier0+team"),     # tier 0 holds 16 members / 8 rows: most centres go to the team tier
-    ((9, 1, 1, 9, 24, 16), "team-only"),          # tier 0 holds one member: every centre with a neighbour is a team job
+    ((11, 16, 8, 12, 512, 256), "tier0+team"),     # tier 0 holds 16 members / 8 rows: most centres go to the team tier
+    ((11, 1, 1, 9, 24, 16), "team-only"),          # tier 0 holds one member: every centre with a neighbour is a team job
 ])
 def test_large_path_every_tier_matches_oracle(cuda_device, large_caps, caps, label):
     from oracle import partition as P
@@ -181,7 +181,7 @@ def test_large_path_powerlaw_sample_matches_oracle(cuda_device, large_caps):
     csr = gen_powerlaw(30000, 150000, seed=2)
     rng = np.random.default_rng(1)
     centres = np.sort(rng.choice(csr.num_nodes, size=64, replace=False)).astype(np.int32)
-    for caps in (DEFAULT_CAPS, (10, 512, 256, 15, 16384, 8192)):
+    for caps in (DEFAULT_CAPS, (12, 512, 256, 15, 16384, 8192)):
         large_caps(*caps)
         for depth in (2, 3):
             ref = P.partition_dataset(csr, depth, mode="hetero", centres=centres)
