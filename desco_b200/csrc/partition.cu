@@ -1323,7 +1323,7 @@ int team_count() {  // co-resident teams: the cooperative launch needs every CTA
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, partition_team_kernel, TM_THREADS, 0) != cudaSuccess || per_sm < 1)
       per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 5) per_sm = 5;
     teams = desco_num_sms() * per_sm / TM_CTAS;
     if (teams < 1) teams = 1;
   }
