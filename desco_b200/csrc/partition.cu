@@ -601,7 +601,9 @@ __device__ __forceinline__ bool sorted_lists_intersect(const int32_t* __restrict
   return false;
 }
 
-// ToTconvHetero on an existing packed batch: one warp per row, one lane per incident edge.
+// ToTconvHetero on an existing packed batch: one warp per row, one lane per incident edge.  The type of an edge is
+// symmetric (a common neighbour of u and v), so only the u < v direction intersects the two rows; it then writes the
+// reverse entry too (its position in row v by binary search - rows are sorted and the batch is symmetric).
 __global__ void edge_types_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ edge_col,
                                   int num_rows, uint8_t* __restrict__ edge_tri) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -609,7 +611,17 @@ __global__ void edge_types_kernel(const int32_t* __restrict__ edge_ptr, const in
   const int rb = edge_ptr[row], re = edge_ptr[row + 1];
   for (int e = rb + lane_id(); e < re; e += 32) {
     const int v = edge_col[e];
-    edge_tri[e] = sorted_lists_intersect(edge_col, rb, re, edge_ptr[v], edge_ptr[v + 1]) ? 1 : 0;
+    const int vb = edge_ptr[v], ve = edge_ptr[v + 1];
+    int lo = vb, hi = ve;  // position of `row` in row v
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (edge_col[mid] < row) lo = mid + 1; else hi = mid;
+    }
+    const bool mirrored = lo < ve && edge_col[lo] == row;  // always, for the undirected batches of the partition
+    if (mirrored && v < row) continue;                     // written by row v
+    const uint8_t t = sorted_lists_intersect(edge_col, rb, re, vb, ve) ? 1 : 0;
+    edge_tri[e] = t;
+    if (mirrored && v > row) edge_tri[lo] = t;
   }
 }
 
