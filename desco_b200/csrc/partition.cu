@@ -1002,6 +1002,9 @@ struct TeamArgs {
   const int32_t* big_list; int* big_count; int* ticket;
   TeamCtrl* ctrl; uint8_t* slices; size_t slice_bytes;
   int max_words, max_nodes;
+  // reached lists of the big centres, kept from the count pass so that fill skips both BFS phases (two of its four
+  // adjacency passes); a centre that does not fit (cache_off = -1) is simply recomputed
+  unsigned long long* cache_cursor; int32_t* cache_off; int32_t* cache; long long cache_cap;
   int32_t* status;
 };
 
@@ -1133,16 +1136,20 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
         if (!p.fill) { p.out_nv[ci] = 0; p.out_ne[ci] = 0; p.centre_graph[ci] = gid; }
       }
     } else if (!skip) {
+      const int coff = p.fill ? p.cache_off[ci] : -1;
+      const bool cached = coff >= 0;  // fill: the reached list of the count pass is at hand
       if (rank == 0 && tid == 0) {
-        Mb[cl >> 5] = 1u << (cl & 31);
-        L[0] = centre;
-        c->nL = 1; c->nR = 0; c->cnt = 0;
+        if (!cached) {
+          Mb[cl >> 5] = 1u << (cl & 31);
+          L[0] = centre;
+        }
+        c->nL = cached ? 0 : 1; c->nR = 0; c->cnt = 0;
       }
       sn = team_sync(c, s_snap);
       if (sn.abort) break;
 
       // ---- phase A: k levels of frontier expansion (data.py:329-350) ----
-      int lb = 0, le = 1;
+      int lb = 0, le = cached ? 0 : 1;
       for (int level = 0; level < p.depth && lb < le; ++level) {
         const bool restricted = p.mode == DESCO_MODE_CANONICAL || (p.mode == DESCO_MODE_HETERO && level == p.depth - 1);
         team_rows(rowptr, col, L, lb, le, restricted ? centre : 0x7fffffff, rank, [&](int v, bool ok) {
@@ -1158,10 +1165,19 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
         lb = le;
         le = min(sn.nL, p.max_nodes);
       }
-      const int nL = min(sn.nL, p.max_nodes);
+      const int nL = cached ? 0 : min(sn.nL, p.max_nodes);
 
       // ---- phase B + C: candidates <= centre (data.py:385), component of the centre inside them (:387-390) ----
-      if (p.mode == DESCO_MODE_HETERO) {
+      if (cached) {
+        const int n = p.out_nv[ci];
+        for (int i = tt; i < n; i += TT) {
+          const int v = p.cache[coff + i];
+          R[i] = v;
+          atomicOr(&RP[(v - lo) >> 5].x, 1u << ((v - lo) & 31));
+        }
+        if (rank == 0 && tid == 0) c->nR = n;
+        sn = team_sync(c, s_snap);
+      } else if (p.mode == DESCO_MODE_HETERO) {
         if (rank == 0 && tid == 0) {
           RP[cl >> 5].x = 1u << (cl & 31);
           R[0] = centre;
@@ -1249,7 +1265,18 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
           p.out_ne[ci] = sn.cnt;
           p.out_nv[ci] = sn.cnt > 0 ? nv : 0;  // edge-free neighborhoods are dropped (workload.py:253-256)
           p.centre_graph[ci] = gid;
+          long long off = -1;
+          if (sn.cnt > 0) {
+            off = (long long)atomicAdd(p.cache_cursor, (unsigned long long)nv);
+            if (off + nv > p.cache_cap) off = -1;
+          }
+          p.cache_off[ci] = (int32_t)off;
+          c->chunk_tot[0] = (int)off;
         }
+        sn = team_sync(c, s_snap);
+        const int off = __ldcg(&c->chunk_tot[0]);
+        if (off >= 0)
+          for (int i = tt; i < nv; i += TT) p.cache[off + i] = __ldcg(R + i);
       } else {
         if (n0 == 0 && rank == 0 && tid == 0) p.edge_ptr[0] = 0;
         sn = team_sync(c, s_snap);  // node_gid of every row is in place
@@ -1325,7 +1352,8 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
 int g_sp_log2h0 = 13, g_sp_capl0 = 5120, g_sp_capr0 = 4096;      // tier 0: 32 + 20 + 16 KB of shared memory
 
 struct LargeLayout {
-  size_t klass_off, counters_off, list_off, ctrl_off, slices_off, slice_bytes, bytes;
+  size_t klass_off, counters_off, list_off, coff_off, ctrl_off, slices_off, slice_bytes, cache_off, bytes;
+  long long cache_cap;
   int teams, max_words;
 };
 
@@ -1351,10 +1379,16 @@ LargeLayout large_layout(int max_graph_nodes, int num_centres) {
   l.klass_off = 0;
   l.counters_off = up(nc);
   l.list_off = l.counters_off + 256;
-  l.ctrl_off = l.list_off + up(nc * 4);
+  l.coff_off = l.list_off + up(nc * 4);
+  l.ctrl_off = l.coff_off + up(nc * 4);
   l.slices_off = l.ctrl_off + up(sizeof(TeamCtrl) * l.teams);
   l.slice_bytes = up((size_t)l.max_words * 12 + (size_t)max_graph_nodes * 8);
-  l.bytes = l.slices_off + l.slice_bytes * l.teams;
+  l.cache_off = l.slices_off + l.slice_bytes * l.teams;
+  // reached-list cache of the team tier: 16 rows per node of the target graph, between 1M and 64M entries
+  l.cache_cap = (long long)max_graph_nodes * 16;
+  if (l.cache_cap < (1ll << 20)) l.cache_cap = 1ll << 20;
+  if (l.cache_cap > (1ll << 26)) l.cache_cap = 1ll << 26;
+  l.bytes = l.cache_off + up((size_t)l.cache_cap * 4);
   return l;
 }
 
@@ -1409,6 +1443,8 @@ int launch_partition_large(const int32_t* rowptr, const int32_t* col, const int3
     t.big_list = a.big_list; t.big_count = counters; t.ticket = counters + 1;
     t.ctrl = (TeamCtrl*)(base + l.ctrl_off); t.slices = base + l.slices_off; t.slice_bytes = l.slice_bytes;
     t.max_words = l.max_words; t.max_nodes = max_graph_nodes; t.status = status;
+    t.cache_cursor = (unsigned long long*)(counters + 2);  // 8-byte aligned: counters is 256-byte aligned
+    t.cache_off = (int32_t*)(base + l.coff_off); t.cache = (int32_t*)(base + l.cache_off); t.cache_cap = l.cache_cap;
     void* params[] = {(void*)&t};
     DESCO_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)partition_team_kernel, dim3(l.teams * TM_CTAS), dim3(TM_THREADS),
                                                params, 0, stream));
