@@ -672,6 +672,9 @@ struct SparseArgs {
   int32_t* node_gid; int32_t* edge_ptr; int32_t* edge_col;
   uint8_t* klass; int tier;      // centre class: 0 = served by this kernel (shared memory), 1 = handed to the team tier
   int32_t* big_list; int* big_count;  // centres handed to the team tier (appended by the count pass)
+  // sorted reached list + induced degrees of every served centre, kept from the count pass (hetero mode) so that fill
+  // goes straight to the emission; a centre that does not fit the cache (cache_off = -1) is recomputed
+  unsigned long long* cache_cursor; int32_t* cache_off; int32_t* cache; long long cache_cap;
   int log2H, capL, capR;         // hash slots (power of two), member-list / reached-list capacities (capR power of two)
 };
 
@@ -696,6 +699,12 @@ struct SparseSet {
       h = (h + 1) & (H - 1);
     }
   }
+  // v is known to be absent: park it with the "reached" flag set, return its slot
+  __device__ __forceinline__ int insert_reached(int v) {
+    uint32_t h = slot_of(v);
+    while (atomicCAS(&keys[h], SP_EMPTY, (uint32_t)v | SP_FLAG) != SP_EMPTY) h = (h + 1) & (H - 1);
+    return (int)h;
+  }
   __device__ __forceinline__ int find(int v) const {  // slot or -1
     uint32_t h = slot_of(v);
     while (true) {
@@ -717,7 +726,7 @@ __device__ unsigned long long g_sparse_phase_cycles[SPH_COUNT];
 
 __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const SparseArgs p) {
   extern __shared__ uint32_t sp_smem[];
-  __shared__ int s_nL, s_nR, s_over, s_cnt, s_gid;
+  __shared__ int s_nL, s_nR, s_over, s_cnt, s_gid, s_coff;
   SparseSet set;
   set.log2H = p.log2H; set.H = 1 << p.log2H; set.capL = p.capL; set.capR = p.capR;
   set.keys = sp_smem;
@@ -752,9 +761,10 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
       s_gid = a;
     }
     __syncthreads();
-    if (tid == 0) set.insert(centre);
-    __syncthreads();
-
+    const int n0 = p.fill ? p.node_off[ci] : 0;
+    const int eo = p.fill ? p.edge_off[ci] : 0;
+    const int coff = p.fill ? p.cache_off[ci] : -1;
+    int nv = 0;
     long long tick = clock64();
     auto lap = [&](int phase) {
       if (tid == 0) {
@@ -763,6 +773,19 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
         tick = now;
       }
     };
+    if (coff >= 0) {  // fill from the cache: rebuild the hash from the sorted reached list, rows and degrees are at hand
+      nv = p.out_nv[ci];
+      for (int i = tid; i < nv; i += SP_THREADS) {
+        const int v = p.cache[coff + i];
+        set.R[i] = (uint32_t)v;
+        rank16[set.insert_reached(v)] = (uint16_t)i;
+        p.node_gid[n0 + i] = v;
+        p.edge_ptr[n0 + 1 + i] = p.cache[coff + nv + i];
+      }
+      __syncthreads();
+    } else {
+    if (tid == 0) set.insert(centre);
+    __syncthreads();
     // ---- phase A: k levels of frontier expansion (data.py:329-350); one warp per frontier node ----
     int lb = 0, le = 1;
     bool over = false;
@@ -863,7 +886,7 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
 
     lap(SPH_COMPONENT);
     // ---- phase D: sort the reached list -> ascending node ids (canonical node = last row) ----
-    const int nv = s_nR;
+    nv = s_nR;
     int n2 = 1;
     while (n2 < nv) n2 <<= 1;
     for (int i = nv + tid; i < n2; i += SP_THREADS) set.R[i] = 0x7fffffffu;
@@ -887,8 +910,6 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
 
     lap(SPH_SORT);
     // ---- induced degrees (count pass: just the total) ----
-    const int n0 = p.fill ? p.node_off[ci] : 0;
-    const int eo = p.fill ? p.edge_off[ci] : 0;
     if (p.mode == DESCO_MODE_HETERO) {  // degrees were counted by the component BFS
       if (p.fill)
         for (int i = tid; i < nv; i += SP_THREADS) {
@@ -915,6 +936,7 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
         }
       }
     }
+    }  // not cached
     __syncthreads();
     lap(SPH_DEGREE);
     if (!p.fill) {
@@ -924,7 +946,21 @@ __global__ void __launch_bounds__(SP_THREADS) partition_sparse_kernel(const Spar
         p.out_nv[ci] = ne > 0 ? nv : 0;  // edge-free neighborhoods are dropped (workload.py:253-256)
         p.centre_graph[ci] = s_gid;
         p.klass[ci] = 0;
+        long long off = -1;
+        if (ne > 0 && p.mode == DESCO_MODE_HETERO) {
+          off = (long long)atomicAdd(p.cache_cursor, (unsigned long long)(2 * nv));
+          if (off + 2 * nv > p.cache_cap) off = -1;
+        }
+        p.cache_off[ci] = (int32_t)off;
+        s_coff = (int)off;
       }
+      __syncthreads();
+      if (s_coff >= 0)
+        for (int i = tid; i < nv; i += SP_THREADS) {
+          const int u = (int)set.R[i];
+          p.cache[s_coff + i] = u;
+          p.cache[s_coff + nv + i] = (int)rank16[set.find(u)];  // induced degree, still parked beside the slot
+        }
     } else {
       if (n0 == 0 && tid == 0) p.edge_ptr[0] = 0;
       if (warp == 0) {  // in-place inclusive scan of the row degrees
@@ -1384,10 +1420,10 @@ LargeLayout large_layout(int max_graph_nodes, int num_centres) {
   l.slices_off = l.ctrl_off + up(sizeof(TeamCtrl) * l.teams);
   l.slice_bytes = up((size_t)l.max_words * 12 + (size_t)max_graph_nodes * 8);
   l.cache_off = l.slices_off + l.slice_bytes * l.teams;
-  // reached-list cache of the team tier: 16 rows per node of the target graph, between 1M and 64M entries
-  l.cache_cap = (long long)max_graph_nodes * 16;
+  // count -> fill cache of both tiers: 32 entries per node of the target graph, between 1M and 128M entries
+  l.cache_cap = (long long)max_graph_nodes * 32;
   if (l.cache_cap < (1ll << 20)) l.cache_cap = 1ll << 20;
-  if (l.cache_cap > (1ll << 26)) l.cache_cap = 1ll << 26;
+  if (l.cache_cap > (1ll << 27)) l.cache_cap = 1ll << 27;
   l.bytes = l.cache_off + up((size_t)l.cache_cap * 4);
   return l;
 }
@@ -1414,6 +1450,8 @@ int launch_partition_large(const int32_t* rowptr, const int32_t* col, const int3
   a.fill = fill; a.node_off = node_off; a.edge_off = edge_off; a.node_gid = node_gid; a.edge_ptr = edge_ptr; a.edge_col = edge_col;
   a.klass = base + l.klass_off;
   a.big_list = (int32_t*)(base + l.list_off); a.big_count = counters;
+  a.cache_cursor = (unsigned long long*)(counters + 2);  // 8-byte aligned: counters is 256-byte aligned
+  a.cache_off = (int32_t*)(base + l.coff_off); a.cache = (int32_t*)(base + l.cache_off); a.cache_cap = l.cache_cap;
   DescoProfScope prof(DESCO_PROF_PARTITION, stream, 2);
   // the count pass builds the list of big centres; fill reuses it.  Team state (barriers, bitmaps) starts from zero.
   if (!fill) DESCO_CUDA_TRY(cudaMemsetAsync(counters, 0, 256, stream));
