@@ -105,11 +105,12 @@ int desco_partition_batch(const int32_t* rowptr, const int32_t* col, const int32
 
 /* Large-graph variants of passes 1 and 3 (config 5: a 10M-node / 200M-directed-edge target, whose node bitsets no
  * longer fit shared memory; desco_partition_count returns DESCO_ERANGE there).  Same outputs, same reference
- * semantics (data.py:329-396).  The set state of a centre is a hash set + member list: tier 0 in shared memory,
- * tier 1 (balls that overflow it) in a per-CTA slice of `workspace`, and a dense bitset tier for balls that overflow
- * that too.  The SAME workspace (desco_partition_large_workspace_bytes) must be passed to count and to fill,
- * untouched in between: it carries the tier of every centre.  fill also runs the SHMP typing of the whole batch
- * (num_rows = totals[1]). */
+ * semantics (data.py:329-396).  An ordinary centre is served by one CTA with a hash set + member list + reached list
+ * in shared memory; a centre whose ball overflows them by a TEAM of 16 co-resident CTAs (cooperative launch) with
+ * member / reached bitmaps over the target graph in a per-team slice of `workspace`.  The SAME workspace
+ * (desco_partition_large_workspace_bytes) must be passed to count and to fill, untouched in between: it carries the
+ * tier of every centre, the list of team centres and the count pass's reached lists (fill skips the BFS for them).
+ * fill also runs the SHMP typing of the whole batch (num_rows = totals[1]). */
 int64_t desco_partition_large_workspace_bytes(int32_t max_graph_nodes, int32_t num_centres);
 int desco_partition_large_count(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
                                 const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
@@ -121,8 +122,9 @@ int desco_partition_large_fill(const int32_t* rowptr, const int32_t* col, const 
                                const int32_t* node_off, const int32_t* edge_off, int32_t num_rows, int32_t* node_gid,
                                int32_t* edge_ptr, int32_t* edge_col, uint8_t* edge_tri, int32_t* status, void* workspace,
                                int64_t workspace_bytes, void* stream);
-/* Capacities of tier 0 / tier 1 (hash slots as log2, member-list entries, reached-list entries = power of two).
- * Defaults 13/5120/4096 and 19/262144/262144; the tests shrink them to force every tier on small graphs. */
+/* Capacities of the shared-memory tier (hash slots as log2, member-list entries, reached-list entries = power of two;
+ * defaults 13 / 5120 / 4096); the last three arguments are ignored (the team tier has no capacity limit).  The tests
+ * shrink the capacities to force the team tier on small graphs. */
 int desco_partition_large_set_caps(int32_t log2_slots0, int32_t members0, int32_t reached0, int32_t log2_slots1,
                                    int32_t members1, int32_t reached1);
 /* Profiling aid: clock64 cycles thread 0 of every shared-memory-tier CTA spent per phase since the last reset
