@@ -1204,6 +1204,7 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
       const int nL = cached ? 0 : min(sn.nL, p.max_nodes);
 
       // ---- phase B + C: candidates <= centre (data.py:385), component of the centre inside them (:387-390) ----
+      int bfs_cnt = 0;
       if (cached) {
         const int n = p.out_nv[ci];
         for (int i = tt; i < n; i += TT) {
@@ -1227,8 +1228,10 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
             if (ok) {
               const int i = v - lo;
               const uint32_t bit = 1u << (i & 31);
-              if ((__ldcg(Mb + (i >> 5)) & bit) && !(__ldcg(&RP[i >> 5].x) & bit))
-                take = !(atomicOr(&RP[i >> 5].x, bit) & bit);
+              if (__ldcg(Mb + (i >> 5)) & bit) {
+                ++bfs_cnt;  // a member <= centre next to a reached node is reached too: an induced directed edge
+                if (!(__ldcg(&RP[i >> 5].x) & bit)) take = !(atomicOr(&RP[i >> 5].x, bit) & bit);
+              }
             }
             team_append(R, &c->nR, p.max_nodes, v, take);
           });
@@ -1289,11 +1292,12 @@ __global__ void __launch_bounds__(TM_THREADS) partition_team_kernel(const TeamAr
       }
 
       if (!p.fill) {
-        // ---- induced directed edge total ----
-        int cnt = 0;
-        team_rows(rowptr, col, R, 0, nv, limit, rank, [&](int v, bool ok) {
-          if (ok) cnt += (__ldcg(&RP[(v - lo) >> 5].x) >> ((v - lo) & 31)) & 1u;
-        });
+        // ---- induced directed edge total (hetero: already counted by the component BFS) ----
+        int cnt = bfs_cnt;
+        if (p.mode != DESCO_MODE_HETERO)
+          team_rows(rowptr, col, R, 0, nv, limit, rank, [&](int v, bool ok) {
+            if (ok) cnt += (__ldcg(&RP[(v - lo) >> 5].x) >> ((v - lo) & 31)) & 1u;
+          });
         cnt = warp_sum(cnt);
         if (lane == 0 && cnt) atomicAdd(&c->cnt, cnt);
         sn = team_sync(c, s_snap);
