@@ -603,25 +603,70 @@ __device__ __forceinline__ bool sorted_lists_intersect(const int32_t* __restrict
 
 // ToTconvHetero on an existing packed batch: one warp per row, one lane per incident edge.  The type of an edge is
 // symmetric (a common neighbour of u and v), so only the u < v direction intersects the two rows; it then writes the
-// reverse entry too (its position in row v by binary search - rows are sorted and the batch is symmetric).
+// reverse entry too (its position in row v by binary search - rows are sorted and the batch is symmetric).  When BOTH
+// rows are long (hub-hub edges of a power-law ball: a lane would walk thousands of dependent loads) the whole warp
+// takes the edge: 32 elements of the shorter row at a time, each lane one binary search in the longer row.
+constexpr int TYPES_COOP_MIN = 48;  // both rows at least this long -> warp-cooperative intersection
+
 __global__ void edge_types_kernel(const int32_t* __restrict__ edge_ptr, const int32_t* __restrict__ edge_col,
                                   int num_rows, uint8_t* __restrict__ edge_tri) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= num_rows) return;
+  const int lane = lane_id();
   const int rb = edge_ptr[row], re = edge_ptr[row + 1];
-  for (int e = rb + lane_id(); e < re; e += 32) {
-    const int v = edge_col[e];
-    const int vb = edge_ptr[v], ve = edge_ptr[v + 1];
-    int lo = vb, hi = ve;  // position of `row` in row v
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (edge_col[mid] < row) lo = mid + 1; else hi = mid;
+  for (int e0 = rb; e0 < re; e0 += 32) {
+    const int e = e0 + lane;
+    int v = -1, vb = 0, ve = 0, rev = -1;
+    bool mine = false;  // this lane owns the undirected edge (row, v)
+    if (e < re) {
+      v = edge_col[e];
+      vb = edge_ptr[v];
+      ve = edge_ptr[v + 1];
+      int lo = vb, hi = ve;  // position of `row` in row v
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (edge_col[mid] < row) lo = mid + 1; else hi = mid;
+      }
+      const bool mirrored = lo < ve && edge_col[lo] == row;  // always, for the undirected batches of the partition
+      mine = !(mirrored && v < row);                         // otherwise written by row v
+      if (mirrored && v > row) rev = lo;
     }
-    const bool mirrored = lo < ve && edge_col[lo] == row;  // always, for the undirected batches of the partition
-    if (mirrored && v < row) continue;                     // written by row v
-    const uint8_t t = sorted_lists_intersect(edge_col, rb, re, vb, ve) ? 1 : 0;
-    edge_tri[e] = t;
-    if (mirrored && v > row) edge_tri[lo] = t;
+    const bool coop = mine && (re - rb) >= TYPES_COOP_MIN && (ve - vb) >= TYPES_COOP_MIN;
+    if (mine && !coop) {
+      const uint8_t t = sorted_lists_intersect(edge_col, rb, re, vb, ve) ? 1 : 0;
+      edge_tri[e] = t;
+      if (rev >= 0) edge_tri[rev] = t;
+    }
+    uint32_t todo = __ballot_sync(FULL_MASK, coop);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      int sb = rb, se = re;  // shorter list
+      int lb = __shfl_sync(FULL_MASK, vb, src), le = __shfl_sync(FULL_MASK, ve, src);  // longer list
+      if (se - sb > le - lb) {
+        int t0 = sb; sb = lb; lb = t0;
+        t0 = se; se = le; le = t0;
+      }
+      bool hit = false;
+      for (int k0 = sb; k0 < se && !hit; k0 += 32) {
+        bool found = false;
+        if (k0 + lane < se) {
+          const int x = edge_col[k0 + lane];
+          int lo = lb, hi = le;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (edge_col[mid] < x) lo = mid + 1; else hi = mid;
+          }
+          found = lo < le && edge_col[lo] == x;
+        }
+        hit = __any_sync(FULL_MASK, found) != 0;
+      }
+      if (lane == src) {
+        const uint8_t t = hit ? 1 : 0;
+        edge_tri[e] = t;
+        if (rev >= 0) edge_tri[rev] = t;
+      }
+    }
   }
 }
 
