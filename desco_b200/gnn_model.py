@@ -71,6 +71,15 @@ class _PackedWeightsMixin:
         self._invalidate_caches()
         return super().train(mode)
 
+    def _scratch(self, name: str, nbytes: int, device) -> torch.Tensor:
+        """Grow-only scratch buffer owned by the module (kernel workspaces): consecutive launches on one stream may share
+        it, and the step loses a caching-allocator round trip per call.  Not for concurrent use from several streams."""
+        buf = self.__dict__.setdefault("_scratch_bufs", {}).get((name, str(device)))
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes * 1.25), 256), dtype=torch.uint8, device=device)
+            self.__dict__["_scratch_bufs"][(name, str(device))] = buf
+        return buf
+
     def _cached(self, name: str, module: nn.Module, build):
         exact = self.training or torch.is_grad_enabled()
         hit = self._caches.get(name)
@@ -226,7 +235,7 @@ class BaseGNN(_PackedWeightsMixin, nn.Module):
         if G == 0:
             return out
         wbytes = int(lib.desco_shmp_workspace_bytes(V, G, core.layer_num))
-        work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+        work = self._scratch("shmp", wbytes, dev)
         if feat is not None:
             feat = feat.to(device=dev, dtype=torch.float32).contiguous()
             assert feat.shape == (V, core.input_dim)

@@ -167,7 +167,7 @@ class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
         dev = emb_t.device
         out = torch.empty((2 if want_pred else 1, G, Q), dtype=torch.float32, device=dev)
         wb = int(lib.desco_count_head_workspace_bytes(G, Q))
-        work = torch.empty(max(wb, 1), dtype=torch.uint8, device=dev)
+        work = self._scratch("head", max(wb, 1), dev)
         w = self._head_weights()
         precision = PRECISION[self.emb_model.precision]
         w_tc = self._cached("head_tc", self.count_model, lambda: pack_head_weights_tc(self.count_model, self.hidden_dim)) if precision else None
