@@ -1107,7 +1107,7 @@ __device__ __forceinline__ TeamSnap team_sync(TeamCtrl* c, int* s_snap) {
       atomicAdd(&c->bar_gen, 1u);
     } else {
       bool ok = false;  // bounded: a lost team-mate must never hang the GPU box
-      for (unsigned spin = 0; spin < (1u << 23); ++spin) {
+      for (unsigned spin = 0; spin < (1u << 25); ++spin) {
         if (*reinterpret_cast<volatile unsigned*>(&c->bar_gen) != gen) { ok = true; break; }
         __nanosleep(40);
       }
