@@ -103,6 +103,32 @@ def csr_from_networkx(graphs) -> TargetCSR:
     return csr_from_graph_list(out)
 
 
+def load_tu_dataset(root: str, name: str) -> TargetCSR:
+    """Raw TU-format dataset on disk -> one block-diagonal CSR (the ingest of ``data.py:91-232``, which goes through
+    ``torch_geometric.datasets.TUDataset`` + ``T.ToUndirected``, ``main.py:80``): ``<root>/<name>/raw/<name>_A.txt`` (or
+    ``<root>/<name>_A.txt``) holds one ``u, v`` pair of 1-based dataset-wide node ids per line,
+    ``<name>_graph_indicator.txt`` the 1-based graph id of every node.  Nodes of a graph are contiguous and graphs are
+    numbered in file order, so node order inside a graph - what the canonical partition depends on - is the file's."""
+    import os
+
+    for d in (os.path.join(root, name, "raw"), os.path.join(root, name), root):
+        if os.path.exists(os.path.join(d, f"{name}_A.txt")):
+            break
+    else:
+        raise FileNotFoundError(f"{name}_A.txt not found under {root}")
+    gi = np.loadtxt(os.path.join(d, f"{name}_graph_indicator.txt"), dtype=np.int64, ndmin=1)
+    if gi.size == 0 or np.any(np.diff(gi) < 0) or gi[0] != 1:
+        raise ValueError("graph indicator must be 1-based and non-decreasing")
+    n = gi.shape[0]
+    edges = np.loadtxt(os.path.join(d, f"{name}_A.txt"), dtype=np.int64, delimiter=",", ndmin=2) - 1
+    if edges.size and (edges.min() < 0 or edges.max() >= n):
+        raise ValueError("edge endpoint outside the node range")
+    if edges.size and np.any(gi[edges[:, 0]] != gi[edges[:, 1]]):
+        raise ValueError("edge between two different graphs")
+    graph_ptr = np.concatenate([[0], np.cumsum(np.bincount(gi - 1, minlength=int(gi[-1])))])
+    return csr_from_edges(n, edges, graph_ptr)
+
+
 # --------------------------------------------------------------------------------------------
 # seeded synthetic graph families
 # --------------------------------------------------------------------------------------------
