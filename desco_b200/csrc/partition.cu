@@ -715,7 +715,7 @@ struct SparseArgs {
   int32_t* out_nv; int32_t* out_ne; int32_t* centre_graph;
   int fill; const int32_t* node_off; const int32_t* edge_off;
   int32_t* node_gid; int32_t* edge_ptr; int32_t* edge_col;
-  uint8_t* klass; int tier;      // centre class: 0 = served by this kernel (shared memory), 1 = handed to the team tier
+  uint8_t* klass;                // centre class: 0 = served by this kernel (shared memory), 1 = handed to the team tier
   int32_t* big_list; int* big_count;  // centres handed to the team tier (appended by the count pass)
   // sorted reached list + induced degrees of every served centre, kept from the count pass (hetero mode) so that fill
   // goes straight to the emission; a centre that does not fit the cache (cache_off = -1) is recomputed
@@ -1509,7 +1509,7 @@ int launch_partition_large(const int32_t* rowptr, const int32_t* col, const int3
   for (int t = 0; t < l.teams; ++t)
     DESCO_CUDA_TRY(cudaMemsetAsync(base + l.slices_off + (size_t)t * l.slice_bytes, 0, (size_t)l.max_words * 12, stream));
   {  // tier 0: shared memory
-    a.tier = 0; a.log2H = g_sp_log2h0; a.capL = g_sp_capl0; a.capR = g_sp_capr0;
+    a.log2H = g_sp_log2h0; a.capL = g_sp_capl0; a.capR = g_sp_capr0;
     const size_t hslots = (size_t)1 << a.log2H;
     const size_t smem = (hslots + (hslots / 2 > (size_t)a.capL ? hslots / 2 : (size_t)a.capL) + a.capR) * 4;
     if (smem > 200 * 1024) return DESCO_EINVAL;
