@@ -110,6 +110,8 @@ SIGNATURES = {
     "desco_gossip_prepare_queries": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
     "desco_gossip_layer0": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP]),
     "desco_gossip_layer1": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _VP, _I, _VP, _L, _VP]),
+    "desco_gossip_layer0_grouped": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _I, _L, _VP]),
+    "desco_gossip_layer1_group": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _I, _I, _VP, _L, _VP]),
     "desco_gossip_layer1_workspace_bytes": (_L, [_I, _I, _I]),
     "desco_shmp_fused_phase_cycles": (_I, [_VP, _I]),
     "desco_train_plan": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP]),
@@ -150,7 +152,7 @@ def load(auto_build: bool = True) -> ctypes.CDLL:
 
 
 class DescoError(RuntimeError):
-    pass
+    code = 0
 
 
 _ERR = {-22: "EINVAL (bad argument)", -12: "ENOMEM", -5: "ECUDA (CUDA runtime error)", -34: "ERANGE (size limit exceeded)",
@@ -158,8 +160,11 @@ _ERR = {-22: "EINVAL (bad argument)", -12: "ENOMEM", -5: "ECUDA (CUDA runtime er
 
 
 ENOBUFS = -105
+ERANGE = -34
 
 
 def check(code: int, what: str) -> None:
     if code != 0:
-        raise DescoError(f"{what} failed: {code} {_ERR.get(code, '')}")
+        err = DescoError(f"{what} failed: {code} {_ERR.get(code, '')}")
+        err.code = code
+        raise err

@@ -92,10 +92,19 @@ __global__ void gossip_query_kernel(const float* __restrict__ qemb, int Q, const
   }
 }
 
+// s4 layout: the queries are cut into groups of QG consecutive queries; group g is a dense [n_rows][qc_g] block of float4
+// (qc_g = min(QG, Q - g*QG)) at float4 offset g*QG*n_rows.  QG >= Q is the plain [N][Q] layout.  A sharded forward
+// all-gathers and consumes one group at a time (desco_b200/distributed.py), so the blocks must be contiguous.
+__device__ __forceinline__ size_t s4_index(int i, int q, int Q, int QG, long long n_rows) {
+  const int q0 = (q / QG) * QG;
+  const int qc = min(QG, Q - q0);
+  return (size_t)q0 * (size_t)n_rows + (size_t)i * qc + (q - q0);
+}
+
 // layer 0: scalar gated SpMV for all queries; one warp per node, lane = query
 __global__ void gossip_layer0_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int node_begin,
                                      int node_end, const float* __restrict__ x, int Q, const float* __restrict__ qvec,
-                                     float4* __restrict__ S4) {
+                                     float4* __restrict__ S4, int QG, long long n_rows) {
   const int i = node_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (i >= node_end) return;
   const int lane = lane_id();
@@ -117,7 +126,7 @@ __global__ void gossip_layer0_kernel(const int32_t* __restrict__ rowptr, const i
       o.y = g0 * s_lt + (1.f - g0) * s_gt;  // smix (layer 0)
       o.z = x[(size_t)i * Q + q];           // c_i
       o.w = g1 * dl + (1.f - g1) * dg;      // dmix (layer 1)
-      S4[(size_t)i * Q + q] = o;
+      S4[s4_index(i, q, Q, QG, n_rows)] = o;
     }
   }
 }
@@ -140,8 +149,9 @@ __device__ __forceinline__ void zero_acc(float acc[4][4]) {
 // layer 1 + post_mp for a tile of 64 nodes x 1 query
 __global__ void __launch_bounds__(THREADS, 2) gossip_layer1_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int node_begin, int node_end,
-    const float4* __restrict__ S4, int Q, const float* __restrict__ qvec, const float* __restrict__ wg,
-    float* __restrict__ out) {
+    const float4* __restrict__ S4, int Q, int q_begin, const float* __restrict__ qvec, const float* __restrict__ wg,
+    float* __restrict__ out, int ldo) {
+  // S4: one query group [.][Q] (Q = queries of the group, q_begin = its first query); out[i * ldo + local query]
   extern __shared__ __align__(16) float smem[];
   float* X = smem;                 // [TM][LDX]: cols 0-63 u / y1, 64-127 x1 / y2, 128-191 x2
   float* sW = X + TM * LDX;        // [128][64]
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 2) gossip_layer1_kernel(
   const int ty = tid >> 4, tx = tid & 15;
   const int q = blockIdx.x % Q;
   const int i0 = node_begin + (blockIdx.x / Q) * TM;
-  const float* qv = qvec + (size_t)q * QV;
+  const float* qv = qvec + (size_t)(q_begin + q) * QV;
   const float g1 = qv[3 * F + 1];
 
   // per-lane constants of x1 = relu(dmix*alpha + smix*beta + gamma + c*delta)
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 2) gossip_layer1_kernel(
     v += __shfl_xor_sync(FULL_MASK, v, 1);
     const int r = ty * 4 + i;
     if (tx == 0 && i0 + r < node_end)
-      out[(size_t)(i0 + r) * Q + q] = s_c[r] + v + wg[WG_B3];  // neigh_pred + gossip_pred (lightning_model.py:625)
+      out[(size_t)(i0 + r) * ldo + q] = s_c[r] + v + wg[WG_B3];  // neigh_pred + gossip_pred (lightning_model.py:625)
   }
 }
 
@@ -324,8 +334,8 @@ constexpr int GR = 1;  // rows whose loads are in flight together (more = more c
 
 __global__ void __launch_bounds__(G_THREADS, 5) gossip_gather_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int node_begin, int node_end,
-    const float4* __restrict__ S4, int Q, const float* __restrict__ qvec, const float* __restrict__ wg, long long tile0,
-    uint8_t* __restrict__ stage) {
+    const float4* __restrict__ S4, int Q, int q_begin, const float* __restrict__ qvec, const float* __restrict__ wg,
+    long long tile0, uint8_t* __restrict__ stage) {
   __shared__ float4 s_slot[G_NW * 32];  // per-warp staging of 32 neighbours / per-warp partial sums of a hub row
   __shared__ uint8_t s_hubs[TR];
   __shared__ int s_nhub;
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(G_THREADS, 5) gossip_gather_kernel(
   uint8_t* gA1 = gA0 + SLOT;                               // x1
   float* g_c = reinterpret_cast<float*>(gA1 + SLOT);
   float* g_d1 = g_c + TR;
-  const float* qv = qvec + (size_t)q * QV;
+  const float* qv = qvec + (size_t)(q_begin + q) * QV;
   const float g1 = qv[3 * F + 1];
   const float2 alpha = *reinterpret_cast<const float2*>(qv + 2 * lane);
   const float2 gamma = *reinterpret_cast<const float2*>(qv + F + 2 * lane);
@@ -515,8 +525,9 @@ enum { GPH_LOAD = 0, GPH_X2, GPH_Y1, GPH_Y2, GPH_Y4, GPH_SPARE, GPH_COUNT };
 __device__ unsigned long long g_phase_cycles[GPH_COUNT];
 
 __global__ void __launch_bounds__(THREADS_TC, 1) gossip_chain_kernel(
-    int node_begin, int node_end, int Q, const float* __restrict__ qvec, const float* __restrict__ wg, long long tile0,
-    int num_tiles, const uint8_t* __restrict__ stage, float* __restrict__ out) {
+    int node_begin, int node_end, int Q, int q_begin, const float* __restrict__ qvec, const float* __restrict__ wg,
+    long long tile0, int num_tiles, const uint8_t* __restrict__ stage, float* __restrict__ out, int ldo,
+    int* __restrict__ ticket) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem + SM_B;
@@ -534,6 +545,7 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_chain_kernel(
   float* s_part = reinterpret_cast<float*>(smem + SM_PART);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);  // [0] weights, [1] MMA done, [2] u slot + c/d1, [3] x1 slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  int* s_next = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if ((int)blockIdx.x >= num_tiles) return;
@@ -631,13 +643,19 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_chain_kernel(
     __syncthreads();
   };
 
-  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+  // tiles are dealt by an atomic ticket (the first one is the CTA's own index): a CTA that starts late - its SM was held
+  // by a collective's kernel running beside this one - simply takes fewer tiles
+  for (int t = blockIdx.x; t < num_tiles;) {
     const long long tile = tile0 + t;
     const int q = (int)(tile % Q);
     const int i0 = node_begin + (int)(tile / Q) * TR;
-    const int tn = t + gridDim.x;  // this CTA's next tile
-    const float* qv = qvec + (size_t)q * QV;
-    __syncthreads();  // previous tile fully retired (s_part, sEta)
+    int tn = num_tiles;  // this CTA's next tile (ISSUER only)
+    const float* qv = qvec + (size_t)(q_begin + q) * QV;
+    __syncthreads();  // previous tile fully retired (s_part, sEta, s_next)
+    if (tid == ISSUER) {
+      tn = (int)gridDim.x + atomicAdd(ticket, 1);
+      *s_next = tn;
+    }
     long long tick = clock64();
     auto lap = [&](int phase) {
       if (tid == 0) {
@@ -712,9 +730,10 @@ __global__ void __launch_bounds__(THREADS_TC, 1) gossip_chain_kernel(
     tc05::fence_before_sync();
     __syncthreads();
     if (cg == 0 && i0 + row < node_end)  // neigh_pred + gossip_pred (lightning_model.py:625)
-      out[(size_t)(i0 + row) * Q + q] =
+      out[(size_t)(i0 + row) * ldo + q] =
           c + ((s_part[row] + s_part[TR + row]) + (s_part[2 * TR + row] + s_part[3 * TR + row])) + b3;
     lap(GPH_Y4);
+    t = *s_next;  // written before the first barrier of this iteration, overwritten after the next one
   }
   if (tid == ISSUER && !weights_ready) tc05::mbar_wait(&bars[0], 0);  // never exit with a bulk copy in flight
   tc05::fence_before_sync();
@@ -735,11 +754,13 @@ extern "C" {
 int64_t desco_gossip_weight_floats(void) { return WG_TOTAL; }
 int64_t desco_gossip_query_weight_floats(void) { return WQ_TOTAL; }
 
+constexpr int64_t L1_TICKET_BYTES = 256;  // head of the layer-1 workspace: the chain kernel's tile ticket
+
 int64_t desco_gossip_layer1_workspace_bytes(int32_t num_nodes, int32_t num_queries, int32_t precision) {
   if (precision != DESCO_PRECISION_BF16X3 || num_nodes <= 0 || num_queries <= 0) return 0;
   long long tiles = (((long long)num_nodes + gtc::TR - 1) / gtc::TR) * num_queries;
   if (tiles > gtc::CHUNK_TILES) tiles = gtc::CHUNK_TILES;
-  return (int64_t)align_up((size_t)tiles * gtc::TILE_BYTES);
+  return L1_TICKET_BYTES + (int64_t)align_up((size_t)tiles * gtc::TILE_BYTES);
 }
 
 int64_t desco_gossip_workspace_bytes(int32_t num_nodes, int32_t num_queries) {
@@ -770,31 +791,45 @@ int desco_gossip_prepare_queries(const float* query_emb, int32_t num_queries, co
   return DESCO_OK;
 }
 
-int desco_gossip_layer0(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end, const float* x,
-                        int32_t num_queries, const float* qvec, float* s4, void* stream) {
-  if (node_begin < 0 || node_end < node_begin || num_queries < 0) return DESCO_EINVAL;
+int desco_gossip_layer0_grouped(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end,
+                                const float* x, int32_t num_queries, const float* qvec, float* s4, int32_t group_size,
+                                int64_t s4_rows, void* stream) {
+  if (node_begin < 0 || node_end < node_begin || num_queries < 0 || group_size < 1 || s4_rows < node_end) return DESCO_EINVAL;
   if (node_end == node_begin || num_queries == 0) return DESCO_OK;
   if (!rowptr || !col || !x || !qvec || !s4) return DESCO_EINVAL;
   const long long threads = (long long)(node_end - node_begin) * 32;
   DescoProfScope prof(DESCO_PROF_GOSSIP_L0, (cudaStream_t)stream);
   gossip_layer0_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      rowptr, col, node_begin, node_end, x, num_queries, qvec, reinterpret_cast<float4*>(s4));
+      rowptr, col, node_begin, node_end, x, num_queries, qvec, reinterpret_cast<float4*>(s4), group_size,
+      (long long)s4_rows);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;
 }
 
-int desco_gossip_layer1(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end, const float* s4,
-                        int32_t num_queries, const float* qvec, const float* w_gossip, float* out, int32_t precision,
-                        void* workspace, int64_t workspace_bytes, void* stream) {
-  if (node_begin < 0 || node_end < node_begin || num_queries < 0) return DESCO_EINVAL;
+int desco_gossip_layer0(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end, const float* x,
+                        int32_t num_queries, const float* qvec, float* s4, void* stream) {
+  return desco_gossip_layer0_grouped(rowptr, col, node_begin, node_end, x, num_queries, qvec, s4,
+                                     num_queries > 0 ? num_queries : 1, node_end, stream);
+}
+
+int desco_gossip_layer1_group(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end,
+                              const float* s4_group, int32_t query_begin, int32_t group_queries, const float* qvec,
+                              const float* w_gossip, float* out, int32_t out_stride, int32_t precision, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+  const int32_t num_queries = group_queries;
+  if (node_begin < 0 || node_end < node_begin || num_queries < 0 || query_begin < 0 || out_stride < num_queries)
+    return DESCO_EINVAL;
   if (precision != DESCO_PRECISION_FP32 && precision != DESCO_PRECISION_BF16X3) return DESCO_EINVAL;
   if (node_end == node_begin || num_queries == 0) return DESCO_OK;
-  if (!rowptr || !col || !s4 || !qvec || !w_gossip || !out) return DESCO_EINVAL;
+  if (!rowptr || !col || !s4_group || !qvec || !w_gossip || !out) return DESCO_EINVAL;
+  const float4* s4 = reinterpret_cast<const float4*>(s4_group);
   if (precision == DESCO_PRECISION_BF16X3) {
     if (!workspace) return DESCO_EINVAL;
     const long long tc_tiles = (((long long)(node_end - node_begin) + gtc::TR - 1) / gtc::TR) * num_queries;
-    const long long cap = workspace_bytes / gtc::TILE_BYTES;  // tiles the staging buffer holds
+    const long long cap = (workspace_bytes - L1_TICKET_BYTES) / gtc::TILE_BYTES;  // tiles the staging buffer holds
     if (cap < 1) return DESCO_ENOMEM;
+    int* ticket = (int*)workspace;
+    uint8_t* stage = (uint8_t*)workspace + L1_TICKET_BYTES;
     static bool tc_attr_set = false;
     if (!tc_attr_set) {
       DESCO_CUDA_TRY(cudaFuncSetAttribute(gtc::gossip_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -804,12 +839,15 @@ int desco_gossip_layer1(const int32_t* rowptr, const int32_t* col, int32_t node_
     const int sms = desco_num_sms();
     for (long long t0 = 0; t0 < tc_tiles; t0 += cap) {
       const int n = (int)(tc_tiles - t0 < cap ? tc_tiles - t0 : cap);
-      DescoProfScope prof(DESCO_PROF_GOSSIP_L1, (cudaStream_t)stream, 2);
-      gtc::gossip_gather_kernel<<<n, gtc::G_THREADS, 0, (cudaStream_t)stream>>>(
-          rowptr, col, node_begin, node_end, reinterpret_cast<const float4*>(s4), num_queries, qvec, w_gossip, t0,
-          (uint8_t*)workspace);
+      DESCO_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), (cudaStream_t)stream));
+      {
+        DescoProfScope prof(DESCO_PROF_GOSSIP_L1, (cudaStream_t)stream, 1);
+        gtc::gossip_gather_kernel<<<n, gtc::G_THREADS, 0, (cudaStream_t)stream>>>(
+            rowptr, col, node_begin, node_end, s4, num_queries, query_begin, qvec, w_gossip, t0, stage);
+      }
+      DescoProfScope prof(DESCO_PROF_GOSSIP_CHAIN, (cudaStream_t)stream, 1);
       gtc::gossip_chain_kernel<<<n < sms ? n : sms, gtc::THREADS_TC, gtc::SMEM_BYTES, (cudaStream_t)stream>>>(
-          node_begin, node_end, num_queries, qvec, w_gossip, t0, n, (const uint8_t*)workspace, out);
+          node_begin, node_end, num_queries, query_begin, qvec, w_gossip, t0, n, stage, out, out_stride, ticket);
       DESCO_LAUNCH_CHECK();
     }
     return DESCO_OK;
@@ -825,9 +863,16 @@ int desco_gossip_layer1(const int32_t* rowptr, const int32_t* col, int32_t node_
   if (blocks > 0x7fffffffLL) return DESCO_ERANGE;
   DescoProfScope prof(DESCO_PROF_GOSSIP_L1, (cudaStream_t)stream);
   gossip_layer1_kernel<<<(unsigned)blocks, THREADS, smem, (cudaStream_t)stream>>>(
-      rowptr, col, node_begin, node_end, reinterpret_cast<const float4*>(s4), num_queries, qvec, w_gossip, out);
+      rowptr, col, node_begin, node_end, s4, num_queries, query_begin, qvec, w_gossip, out, out_stride);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;
+}
+
+int desco_gossip_layer1(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end, const float* s4,
+                        int32_t num_queries, const float* qvec, const float* w_gossip, float* out, int32_t precision,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  return desco_gossip_layer1_group(rowptr, col, node_begin, node_end, s4, 0, num_queries, qvec, w_gossip, out, num_queries,
+                                   precision, workspace, workspace_bytes, stream);
 }
 
 int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_nodes, const float* x,

@@ -1548,9 +1548,21 @@ __global__ void scan_finalize_kernel(const int32_t* __restrict__ centres, const 
                                      const int32_t* __restrict__ node_off, const int32_t* __restrict__ edge_off, int C,
                                      int32_t* __restrict__ nbh_ptr, int32_t* __restrict__ centre_out,
                                      uint8_t* __restrict__ indicator, int32_t* __restrict__ totals,
-                                     int32_t* __restrict__ max_rows) {
+                                     int32_t* __restrict__ max_rows, unsigned long long* __restrict__ sums64) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = i < C;
+  if (sums64) {  // exact row / edge totals (caller-zeroed): the int32 scans above wrap silently past 2^31
+    unsigned long long v = in ? (unsigned long long)nv[i] : 0ull, e = in ? (unsigned long long)ne[i] : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      v += __shfl_xor_sync(FULL_MASK, v, d);
+      e += __shfl_xor_sync(FULL_MASK, e, d);
+    }
+    if (lane_id() == 0 && (v | e)) {
+      atomicAdd(&sums64[0], v);
+      atomicAdd(&sums64[1], e);
+    }
+  }
   if (!in) i = C - 1;  // keep the warp whole for the shuffle below; the duplicate work is idempotent
   bool keep = ne[i] > 0;
   if (indicator) indicator[i] = keep ? 1 : 0;
@@ -1663,7 +1675,8 @@ int desco_partition_scan(const int32_t* centres, const int32_t* nv, const int32_
   DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(workspace, bytes, ne, edge_off, num_centres, s));
   desco_count_launches(1);
   scan_finalize_kernel<<<(num_centres + 255) / 256, 256, 0, s>>>(centres, nv, ne, keep_rank, node_off, edge_off,
-                                                                num_centres, nbh_ptr, centre_out, indicator, totals, nullptr);
+                                                                num_centres, nbh_ptr, centre_out, indicator, totals, nullptr,
+                                                                nullptr);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;
 }
@@ -1683,10 +1696,13 @@ __global__ void __launch_bounds__(1024) scan_small_kernel(const int32_t* __restr
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   if (tid < 3) s_carry[tid] = 0;
   int mx = 0;
+  unsigned long long v64 = 0, e64 = 0;  // exact totals -> totals[8..11] (two u64): the int32 scans wrap past 2^31
   __syncthreads();
   for (int base = 0; base < C; base += 1024) {
     const int i = base + tid;
     const int v = i < C ? nv[i] : 0, e = i < C ? ne[i] : 0, k = e > 0 ? 1 : 0;
+    v64 += (unsigned long long)v;
+    e64 += (unsigned long long)e;
     int sk = warp_incl_scan(k), sv = warp_incl_scan(v), se = warp_incl_scan(e);
     if (lane == 31) { s_w[0][warp] = sk; s_w[1][warp] = sv; s_w[2][warp] = se; }
     __syncthreads();
@@ -1725,6 +1741,16 @@ __global__ void __launch_bounds__(1024) scan_small_kernel(const int32_t* __restr
   mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 2));
   mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 1));
   if (lane == 0 && mx > 0) atomicMax(&totals[3], mx);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v64 += __shfl_xor_sync(FULL_MASK, v64, d);
+    e64 += __shfl_xor_sync(FULL_MASK, e64, d);
+  }
+  if (lane == 0) {
+    unsigned long long* sums64 = reinterpret_cast<unsigned long long*>(totals + 8);
+    atomicAdd(&sums64[0], v64);
+    atomicAdd(&sums64[1], e64);
+  }
 }
 }  // namespace
 
@@ -1775,16 +1801,24 @@ int desco_partition_batch(const int32_t* rowptr, const int32_t* col, const int32
     bytes = (size_t)scan_bytes;
     DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_ws, bytes, ne, eoff, num_centres, s));
     scan_finalize_kernel<<<(num_centres + 255) / 256, 256, 0, s>>>(centres, nv, ne, rank, noff, eoff, num_centres, nbh_ptr,
-                                                                  centre_out, indicator, small, small + 3);
+                                                                  centre_out, indicator, small, small + 3,
+                                                                  reinterpret_cast<unsigned long long*>(small + 8));
   }
   DESCO_LAUNCH_CHECK();
   // the one host sync of the path: output sizes (and the device status word) through a pinned staging buffer
   static thread_local int32_t* pinned = nullptr;
   if (!pinned) DESCO_CUDA_TRY(cudaHostAlloc((void**)&pinned, 64, cudaHostAllocDefault));
-  DESCO_CUDA_TRY(cudaMemcpyAsync(pinned, small, 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  DESCO_CUDA_TRY(cudaMemcpyAsync(pinned, small, 12 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   DESCO_CUDA_TRY(cudaStreamSynchronize(s));
   for (int i = 0; i < 4; ++i) totals_host[i] = pinned[i];
   if (pinned[4] != 0) return pinned[4];
+  {  // exact totals: a packed batch addresses rows and edges with int32 - the caller must split the centre list
+    const unsigned long long* sums64 = reinterpret_cast<const unsigned long long*>(pinned + 8);
+    if (sums64[0] > 0x7fffffffull || sums64[1] > 0x7fffffffull) {
+      totals_host[1] = totals_host[2] = -1;
+      return DESCO_ERANGE;
+    }
+  }
   if (pinned[1] > cap_rows || pinned[2] > cap_edges) return DESCO_ENOBUFS;  // caller re-allocates from totals_host
   if (pinned[1] == 0) {
     if (edge_ptr) DESCO_CUDA_TRY(cudaMemsetAsync(edge_ptr, 0, sizeof(int32_t), s));

@@ -231,9 +231,13 @@ def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: in
             _ptr(centres), _ptr(nv), _ptr(ne), C, _ptr(rank), _ptr(noff), _ptr(eoff), _ptr(nbh_ptr), _ptr(centre_out),
             _ptr(indicator), _ptr(totals), _ptr(work), wbytes, st), "desco_partition_scan")
         mx = nv[:C].max().reshape(1) if C else torch.zeros(1, **i32)
-        G, V, E, code, max_nv = (int(x) for x in torch.cat([small, mx]).cpu())  # the one host sync: output sizes
+        sums = torch.stack([nv[:C].sum(dtype=torch.int64), ne[:C].sum(dtype=torch.int64)])  # exact: the scans are int32
+        G, V, E, code, max_nv, V64, E64 = (int(x) for x in torch.cat([small.long(), mx.long(), sums]).cpu())  # the one host sync
         if code != 0:
             _lib.check(code, "partition kernel (device status)")
+        if V64 >= 2**31 or E64 >= 2**31:
+            _lib.check(_lib.ERANGE, f"partition_batch: {V64} rows / {E64} edges do not fit one packed batch (int32 offsets); "
+                                    "split the centre list (partition_batches does)")
         node_gid = torch.empty(V, **i32)
         edge_ptr = torch.zeros(V + 1, **i32)
         edge_col = torch.empty(E, **i32)
@@ -257,6 +261,35 @@ def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: in
     if large:
         batch._cache["tier"] = lwork[:C].clone()  # which tier served each centre (0 shared-memory hash, 1 team bitmap)
     return batch
+
+
+def partition_batches(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: int, mode: Union[int, str] = "hetero",
+                      max_centres: Optional[int] = None, large: Optional[bool] = None):
+    """``partition_batch`` over consecutive chunks of ``centres`` (generator of packed batches, in centre order).
+
+    A packed batch addresses rows and edges with int32, and on a power-law target the depth-2 ball of a hub holds 1e5-1e6
+    rows, so a long centre list (a rank's whole centre range, ``distributed.ShardedPipeline``) cannot go through one
+    call.  ``max_centres`` bounds a chunk (default: 4096 in the large-graph regime, 1 << 20 otherwise); a chunk whose
+    exact row or edge total still overflows (``DESCO_ERANGE``) is halved and retried."""
+    dev = graph.rowptr.device
+    if large is None:
+        large = graph.max_graph_nodes > LARGE_GRAPH_NODES
+    if centres is None:
+        centres = torch.arange(graph.num_nodes, dtype=torch.int32, device=dev)
+    centres = centres.to(device=dev, dtype=torch.int32).contiguous()
+    step = int(max_centres) if max_centres else (4096 if large else 1 << 20)
+    todo = [(a, min(a + step, centres.numel())) for a in range(0, centres.numel(), step)][::-1]
+    while todo:
+        a, b = todo.pop()
+        try:
+            batch = partition_batch(graph, centres[a:b], depth, mode, large)
+        except _lib.DescoError as e:
+            if e.code != _lib.ERANGE or b - a <= 1:
+                raise
+            mid = (a + b) // 2
+            todo += [(mid, b), (a, mid)]
+            continue
+        yield batch
 
 
 _CAPACITY = {"rows_per_centre": 24.0, "edges_per_row": 6.0}  # running maxima of the batches seen so far

@@ -387,36 +387,82 @@ class GossipBaseGNN(_PackedWeightsMixin, nn.Module):
         return (out, gates) if want_gates else out
 
 
-def _gossip_forward_node_range(self, rowptr, col, x, query_emb, node_begin, node_end, exchange):
-    """Node-range shard of the gossip forward (desco_b200.distributed): layer 0 for [node_begin, node_end) from the
-    replicated counts ``x[N,Q]``, ``exchange`` (all-gather of row blocks) of the layer-0 scalars s4 - the halo - then
-    layer 1 + post_mp for the same range and a final exchange of the output rows.  Returns out[N,Q]."""
-    if self.training:
-        raise NotImplementedError("gossip training is not a CUDA path yet")
-    lib = _lib.load()
-    w = self.packed_weights()
-    dev = w["wg"].device
-    x = x.to(device=dev, dtype=torch.float32).contiguous()
-    query_emb = query_emb.to(device=dev, dtype=torch.float32).contiguous()
-    N, Q = x.shape
-    n_loc = node_end - node_begin
-    qvec = torch.empty((Q, 256), dtype=torch.float32, device=dev)
-    s4_full_local = torch.zeros((N, Q, 4), dtype=torch.float32, device=dev) if n_loc else torch.zeros((0, Q, 4), device=dev)
-    with torch.cuda.device(dev):
-        st = _stream()
-        _lib.check(lib.desco_gossip_prepare_queries(_ptr(query_emb), Q, _ptr(w["wq"]), _ptr(qvec), 0, st), "gossip_prepare_queries")
-        if n_loc:
-            _lib.check(lib.desco_gossip_layer0(_ptr(rowptr), _ptr(col), node_begin, node_end, _ptr(x), Q, _ptr(qvec),
-                                               _ptr(s4_full_local), st), "gossip_layer0")
-        s4 = exchange(s4_full_local[node_begin:node_end].contiguous()).contiguous()  # halo exchange -> s4[N,Q,4] everywhere
-        out_full = torch.zeros((N, Q), dtype=torch.float32, device=dev)
-        if n_loc:
-            sb = int(lib.desco_gossip_layer1_workspace_bytes(n_loc, Q, PRECISION[self.precision]))
-            stage = torch.empty(max(sb, 1), dtype=torch.uint8, device=dev)
-            _lib.check(lib.desco_gossip_layer1(_ptr(rowptr), _ptr(col), node_begin, node_end, _ptr(s4), Q, _ptr(qvec),
-                                               _ptr(w["wg"]), _ptr(out_full), PRECISION[self.precision], _ptr(stage), sb, st),
-                       "gossip_layer1")
-    return exchange(out_full[node_begin:node_end].contiguous())
+class GossipShardedRun:
+    """One node-range-sharded gossip forward of one rank (the reference has no multi-GPU gossip,
+    ``main.py:353-356``).  ``x[N, Q]`` is replicated (the hand-off all-gather of the counting stage); rank r owns the node
+    rows ``[r * n_loc, (r + 1) * n_loc)``.
+
+    ``start()``: per-query vectors, layer 0 of the own rows for every query (one launch, written in the query-grouped
+    layout of ``desco_gossip_layer0_grouped``), then one in-place all-gather PER QUERY GROUP of the layer-0 scalars - the
+    halo; with random labels on a power-law graph nearly every node is in some rank's halo, so the exchange is dense -
+    issued asynchronously, back to back.
+    ``finish()``: for each group, wait for ITS halo only, run layer 1 + post_mp of the own rows (gather + tcgen05 chain
+    kernels), and hand the group's output rows to an asynchronous all-gather: the halo of group g+1 and the output of
+    group g-1 move over NVLink while group g computes, so only the first halo group and the last output group are exposed.
+    Returns ``out[N, Q]`` (replicated) or, with ``gather_output=False``, the own rows ``[hi - lo, Q]``."""
+
+    def __init__(self, model: "GossipBaseGNN", rowptr, col, x, query_emb, comm, query_group: int = 4, gather_output: bool = True):
+        from .distributed import gossip_shard_plan
+
+        if model.training:
+            raise NotImplementedError("gossip training is not a CUDA path yet")
+        self.m, self.rowptr, self.col, self.comm, self.gather_output = model, rowptr, col, comm, gather_output
+        self.lib = _lib.load()
+        self.w = model.packed_weights()
+        self.dev = dev = self.w["wg"].device
+        self.x = x.to(device=dev, dtype=torch.float32).contiguous()
+        self.qe = query_emb.to(device=dev, dtype=torch.float32).contiguous()
+        self.N, self.Q = self.x.shape
+        self.plan = gossip_shard_plan(self.N, self.Q, comm.world, query_group)
+        self.lo, self.hi = self.plan.ranges[comm.rank]
+        self.halo_work: List = []
+
+    def start(self):
+        lib, w, dev, plan = self.lib, self.w, self.dev, self.plan
+        N, Q = self.N, self.Q
+        self.qvec = torch.empty((Q, 256), dtype=torch.float32, device=dev)
+        self.s4 = torch.empty(plan.n_rows * Q * 4, dtype=torch.float32, device=dev)  # grouped [g][n_rows][qc][4]
+        with torch.cuda.device(dev):
+            st = _stream()
+            _lib.check(lib.desco_gossip_prepare_queries(_ptr(self.qe), Q, _ptr(w["wq"]), _ptr(self.qvec), 0, st),
+                       "desco_gossip_prepare_queries")
+            if self.hi > self.lo:
+                _lib.check(lib.desco_gossip_layer0_grouped(_ptr(self.rowptr), _ptr(self.col), self.lo, self.hi, _ptr(self.x), Q,
+                                                           _ptr(self.qvec), _ptr(self.s4), plan.query_group, plan.n_rows, st),
+                           "desco_gossip_layer0_grouped")
+        self.s4_groups = [self.s4[4 * q0 * plan.n_rows: 4 * q1 * plan.n_rows].view(plan.n_rows, q1 - q0, 4) for q0, q1 in plan.groups]
+        self.halo_work = [self.comm.all_gather_block(b, plan.n_loc, ("s4", gi)) for gi, b in enumerate(self.s4_groups)]
+        return self
+
+    def finish(self) -> torch.Tensor:
+        lib, w, dev, plan = self.lib, self.w, self.dev, self.plan
+        N, Q = self.N, self.Q
+        prec = PRECISION[self.m.precision]
+        n_own = self.hi - self.lo
+        out = torch.empty(plan.n_rows * Q, dtype=torch.float32, device=dev)  # grouped [g][n_rows][qc]
+        out_groups = [out[q0 * plan.n_rows: q1 * plan.n_rows].view(plan.n_rows, q1 - q0) for q0, q1 in plan.groups]
+        sb = int(lib.desco_gossip_layer1_workspace_bytes(max(n_own, 1), plan.query_group, prec))
+        stage = self.m._scratch("gossip_l1", max(sb, 1), dev)
+        out_work = []
+        with torch.cuda.device(dev):
+            st = _stream()
+            for (q0, q1), s4g, og, hw in zip(plan.groups, self.s4_groups, out_groups, self.halo_work):
+                hw.wait()  # the current stream waits for this group's halo only
+                if n_own:
+                    _lib.check(lib.desco_gossip_layer1_group(_ptr(self.rowptr), _ptr(self.col), self.lo, self.hi, _ptr(s4g), q0,
+                                                             q1 - q0, _ptr(self.qvec), _ptr(w["wg"]), _ptr(og), q1 - q0, prec,
+                                                             _ptr(stage), sb, st), "desco_gossip_layer1_group")
+                if self.gather_output:
+                    out_work.append(self.comm.all_gather_block(og, plan.n_loc, ("out", q0)))
+        if not self.gather_output:
+            return torch.cat([og[self.lo:self.hi] for og in out_groups], dim=1)
+        for wk in out_work:
+            wk.wait()
+        return torch.cat([og[:N] for og in out_groups], dim=1)
 
 
-GossipBaseGNN.forward_node_range = _gossip_forward_node_range
+def _gossip_forward_sharded(self, rowptr, col, x, query_emb, comm, query_group: int = 4, gather_output: bool = True):
+    return GossipShardedRun(self, rowptr, col, x, query_emb, comm, query_group, gather_output).start().finish()
+
+
+GossipBaseGNN.forward_sharded = _gossip_forward_sharded

@@ -41,8 +41,9 @@ const char* desco_version(void);
 #define DESCO_PROF_SHMP_LAYER 1  /* shmp_layer_kernel (one launch per SHMP layer)  */
 #define DESCO_PROF_SHMP_OTHER 2  /* plan, pre, cvec, pool, readout MLPs, count head */
 #define DESCO_PROF_GOSSIP_L0 3   /* gossip layer-0 scalar sweep                    */
-#define DESCO_PROF_GOSSIP_L1 4   /* gossip layer-1 + post_mp tile kernel           */
-#define DESCO_PROF_SLOTS 5
+#define DESCO_PROF_GOSSIP_L1 4   /* gossip layer 1: gated-sweep gather kernel (FFMA path: the whole tile kernel) */
+#define DESCO_PROF_GOSSIP_CHAIN 5 /* gossip layer 1 + post_mp: tcgen05 GEMM-chain kernel */
+#define DESCO_PROF_SLOTS 6
 int64_t desco_kernel_launches(void);
 int desco_profile_enable(int32_t on);
 int desco_profile_read(double* ms, int64_t* launches);
@@ -73,7 +74,8 @@ int64_t desco_partition_scan_workspace_bytes(int32_t num_centres);
 
 /* Pass 2: exclusive scans.  keep_rank/node_off/edge_off [num_centres]; nbh_ptr[num_centres+1] (first G+1 used);
  * centre_out[num_centres] (first G used); indicator[num_centres] (uint8, may be NULL) == nx_neighs_indicator;
- * totals[3] = {G kept neighborhoods, V rows, E directed edges}. */
+ * totals[3] = {G kept neighborhoods, V rows, E directed edges} - int32 scans: a caller that may pass more than 2^31
+ * rows or edges worth of centres must check sum(nv), sum(ne) in 64 bits first (desco_b200.data.partition_batch does). */
 int desco_partition_scan(const int32_t* centres, const int32_t* nv, const int32_t* ne, int32_t num_centres,
                          int32_t* keep_rank, int32_t* node_off, int32_t* edge_off, int32_t* nbh_ptr,
                          int32_t* centre_out, uint8_t* indicator, int32_t* totals, void* workspace,
@@ -94,7 +96,8 @@ int desco_partition_fill(const int32_t* rowptr, const int32_t* col, const int32_
  * centre_graph [num_centres]) and the packed batch at a capacity of its choice (node_gid[cap_rows],
  * edge_ptr[cap_rows+1], edge_col / edge_tri [cap_edges]).  totals_host[4] (host memory) receives {G, V, E, rows of the
  * largest neighborhood}.  Returns DESCO_ENOBUFS, with totals_host filled and nothing emitted, when V > cap_rows or
- * E > cap_edges: re-allocate and call again. */
+ * E > cap_edges: re-allocate and call again.  Returns DESCO_ERANGE (totals_host[1] = totals_host[2] = -1) when the exact
+ * 64-bit row or edge total of the centre list does not fit the batch's int32 offsets: split the centre list. */
 int64_t desco_partition_batch_workspace_bytes(int32_t num_centres);
 int desco_partition_batch(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
                           const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
@@ -221,9 +224,24 @@ int desco_gossip_layer0(const int32_t* rowptr, const int32_t* col, int32_t node_
 int desco_gossip_layer1(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end, const float* s4,
                         int32_t num_queries, const float* qvec, const float* w_gossip, float* out, int32_t precision,
                         void* workspace, int64_t workspace_bytes, void* stream);
+/* Query-grouped forms for the node-range-sharded forward (desco_b200/distributed.py; the reference has no multi-GPU
+ * gossip, main.py:353-356).  The queries are cut into groups of `group_size` consecutive queries and s4 is laid out
+ * group by group: group g is a dense [s4_rows][qc_g][4] block (qc_g = min(group_size, Q - g*group_size)) at float
+ * offset 4*g*group_size*s4_rows, so that one group of one node range is a contiguous send buffer and the gathered group
+ * a contiguous [s4_rows][qc_g][4] block: the halo all-gather of group g+1 runs under layer 1 of group g.
+ * layer0_grouped writes rows [node_begin, node_end) of every group; layer1_group consumes ONE gathered group
+ * (s4_group = that block, queries [query_begin, query_begin + group_queries)) and writes
+ * out[i * out_stride + (q - query_begin)].  group_size >= Q and out_stride = Q give the plain layouts above. */
+int desco_gossip_layer0_grouped(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end,
+                                const float* x, int32_t num_queries, const float* qvec, float* s4, int32_t group_size,
+                                int64_t s4_rows, void* stream);
+int desco_gossip_layer1_group(const int32_t* rowptr, const int32_t* col, int32_t node_begin, int32_t node_end,
+                              const float* s4_group, int32_t query_begin, int32_t group_queries, const float* qvec,
+                              const float* w_gossip, float* out, int32_t out_stride, int32_t precision, void* workspace,
+                              int64_t workspace_bytes, void* stream);
 /* Staging bytes desco_gossip_layer1 wants for a range of num_nodes nodes (0 for DESCO_PRECISION_FP32; for
- * DESCO_PRECISION_BF16X3 the operand images of up to 8192 tiles of 128 nodes x 1 query, 65 KB each - any multiple of one
- * tile works, the range is walked in chunks). */
+ * DESCO_PRECISION_BF16X3 a 256-byte head + the operand images of up to 8192 tiles of 128 nodes x 1 query, 65 KB each -
+ * any whole number of tiles works, the range is walked in chunks). */
 int64_t desco_gossip_layer1_workspace_bytes(int32_t num_nodes, int32_t num_queries, int32_t precision);
 int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_nodes, const float* x,
                          int32_t num_queries, const float* query_emb, const float* w_gossip,

@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from desco_b200.distributed import all_gather_rows, balanced_shards, node_ranges, shard_range
+from desco_b200.distributed import (LocalComm, ProcessGroupComm, all_gather_rows, balanced_shards, centre_work_estimate,
+                                    gossip_shard_plan, node_ranges, shard_range)
 
 
 def test_shard_ranges_cover_without_overlap():
@@ -32,6 +33,52 @@ def test_balanced_shards_balance_weight():
         tot = np.array([w[a:b].sum() for a, b in sh])
         assert tot.max() / tot.mean() < 1.05 + w.max() / tot.mean()
     assert balanced_shards(np.zeros(0), 4) == [(0, 0)] * 4
+
+
+def test_gossip_shard_plan_geometry():
+    for n, q, world, qg in ((1000, 29, 2, 4), (1_000_000, 29, 8, 4), (5, 3, 4, 8), (128 * 8, 29, 8, 5)):
+        plan = gossip_shard_plan(n, q, world, qg)
+        assert plan.n_loc % 128 == 0 and plan.n_rows == plan.n_loc * world >= n
+        assert plan.ranges[0][0] == 0 and plan.ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(plan.ranges[:-1], plan.ranges[1:]))
+        assert all(0 <= hi - lo <= plan.n_loc for lo, hi in plan.ranges)
+        assert plan.groups[0][0] == 0 and plan.groups[-1][1] == q
+        assert all(a[1] == b[0] for a, b in zip(plan.groups[:-1], plan.groups[1:]))
+        assert max(b - a for a, b in plan.groups) == min(qg, q)
+        assert plan.halo_bytes() == 16 * q * plan.n_loc * (world - 1)
+
+
+def test_local_comm_emulates_the_block_all_gather():
+    comm = LocalComm(3)
+    n_loc = 4
+    bufs = []
+    for r in range(3):
+        b = torch.zeros(3 * n_loc, 2)
+        b[r * n_loc:(r + 1) * n_loc] = r + 1
+        bufs.append(b)
+    works = [comm.for_rank(r).all_gather_block(bufs[r], n_loc, "t") for r in range(3)]
+    for w in works:
+        w.wait()
+    want = torch.arange(1, 4).repeat_interleave(n_loc).view(-1, 1).repeat(1, 2).float()
+    assert all(torch.equal(b, want) for b in bufs)
+
+
+def test_centre_work_estimate_tracks_ball_and_position():
+    from types import SimpleNamespace
+
+    # star: node 9 is the hub of 0..8; path 10-11
+    edges = [(9, i) for i in range(9)] + [(10, 11)]
+    n = 12
+    adj = [[] for _ in range(n)]
+    for a, b in edges:
+        adj[a].append(b)
+        adj[b].append(a)
+    rowptr = torch.tensor(np.cumsum([0] + [len(a) for a in adj]), dtype=torch.int32)
+    col = torch.tensor([v for a in adj for v in sorted(a)], dtype=torch.int32)
+    g = SimpleNamespace(rowptr=rowptr, col=col, num_graphs=1, graph_ptr=torch.tensor([0, n], dtype=torch.int32))
+    w1, w2 = centre_work_estimate(g, 1), centre_work_estimate(g, 2)
+    assert w1[9] > w1[8] and w2[0] > w1[0]  # leaves see the hub's adjacency only from depth 2 on
+    assert np.isclose(w2[0] / (0.25 + 0.0), 1 + 1 + 9) and np.isclose(w2[9] / (0.25 + 0.75 * 9 / 12), 1 + 9 + 9)
 
 
 def _free_port():
@@ -68,6 +115,19 @@ def _worker(rank, world, port, q):
         ref = torch.zeros(N, Q)
         ref[1::2] = (torch.arange(1, N, 2).float() * 10).view(-1, 1)
         assert torch.equal(x, ref)
+        # the in-place block all-gather of the sharded gossip forward (one per query group), issued asynchronously
+        plan = gossip_shard_plan(300, 7, world, 3)
+        comm = ProcessGroupComm()
+        assert (comm.rank, comm.world) == (rank, world)
+        blocks = []
+        for gi, (q0, q1) in enumerate(plan.groups):
+            full = torch.zeros(plan.n_rows, q1 - q0, 4)
+            full[rank * plan.n_loc:(rank + 1) * plan.n_loc] = 10 * (rank + 1) + gi
+            blocks.append((full, comm.all_gather_block(full, plan.n_loc, ("s4", gi))))
+        for gi, (full, work) in enumerate(blocks):
+            work.wait()
+            for r in range(world):
+                assert torch.all(full[r * plan.n_loc:(r + 1) * plan.n_loc] == 10 * (r + 1) + gi)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))

@@ -145,3 +145,30 @@ def test_homog_sage_oracle_matches_reference_golden(golden_dir):
         pooled = torch.zeros(G, emb.shape[1]).index_add_(0, bvec, emb)
         out = oc.post_mp(pooled)
     assert torch.allclose(out, torch.from_numpy(z["out"]), rtol=1e-5, atol=1e-6)
+
+
+def test_large_graph_views_agree_with_the_whole_graph_oracle():
+    """oracle/large.py (ball view for the partition, 2-hop closure for gossip) == the oracle on the whole graph."""
+    import torch
+
+    from desco_b200.graph import gen_powerlaw
+    from oracle import model as M
+    from oracle.large import BallView, gossip_closure
+
+    csr = gen_powerlaw(1500, 6000, seed=2)
+    centres = np.array([3, 700, 1499, 42])
+    full = P.partition_dataset(csr, 2, mode="hetero", centres=centres)
+    view = P.partition_dataset(BallView(csr.rowptr, csr.col, centres, 2), 2, mode="hetero", centres=centres)
+    for k in full:
+        assert np.array_equal(full[k], view[k]), k
+    torch.manual_seed(0)
+    og = M.GossipCountingModel()
+    Q = 3
+    x = torch.floor(torch.exp(torch.randn(csr.num_nodes, Q)))
+    og.set_query_emb(torch.randn(Q, 64))
+    sample = np.array([5, 900, 1499, 0])
+    nodes, ei, pos = gossip_closure(csr.rowptr, csr.col, sample)
+    with torch.no_grad():
+        ref = og.graph_to_count(x, torch.from_numpy(csr.edge_index()))[torch.as_tensor(sample)]
+        got = og.graph_to_count(x[torch.as_tensor(nodes)], torch.from_numpy(ei))[torch.as_tensor(pos)]
+    assert (ref - got).abs().max().item() <= 1e-5

@@ -102,25 +102,20 @@ def test_sharded_pipeline_single_rank_equals_direct(cuda_device):
     with torch.no_grad():
         ref = pg.graph_to_count(SimpleNamespace(graph=g, x=x))
     assert torch.equal(out, ref)
-    # three "ranks" emulated in one process: each computes its node range; the exchange stitches the blocks
-    N = g.num_nodes
-    ranges = node_ranges(N, 3)
-    s4_blocks, out_blocks = {}, {}
+    # three "ranks" emulated in one process (LocalComm): every rank runs the pipelined node-range forward over query
+    # groups; the in-place block exchange stands in for the NCCL all-gathers
+    from desco_b200.distributed import LocalComm
+    from desco_b200.gnn_model import GossipShardedRun
 
-    def run(rank, stage_store):
-        lo, hi = ranges[rank]
-        calls = []
-
-        def exchange(t):
-            calls.append(t)
-            if len(calls) == 1:  # halo scalars: use the blocks every rank computed in the first sweep
-                return torch.cat([stage_store[r] for r in range(3)], 0) if len(stage_store) == 3 else torch.zeros(N, *t.shape[1:], device=t.device).index_copy_(0, torch.arange(lo, hi, device=t.device), t)
-            return t
-        res = pg.emb_model.forward_node_range(g.rowptr, g.col, x, qe, lo, hi, exchange)
-        return calls[0], res
-
-    for r in range(3):  # sweep 1: collect every rank's s4 block
-        s4_blocks[r], _ = run(r, {})
-    for r in range(3):  # sweep 2: with the full halo available
-        _, out_blocks[r] = run(r, s4_blocks)
-    assert torch.equal(torch.cat([out_blocks[r] for r in range(3)], 0), ref)
+    for qg in (4, 29, 5):
+        comm = LocalComm(3)
+        runs = [GossipShardedRun(pg.emb_model, g.rowptr, g.col, x, qe, comm.for_rank(r), query_group=qg) for r in range(3)]
+        for r in runs:
+            r.start()
+        outs = [r.finish() for r in runs]
+        for o in outs:
+            assert torch.equal(o, ref)
+    comm = LocalComm(2)
+    runs = [GossipShardedRun(pg.emb_model, g.rowptr, g.col, x, qe, comm.for_rank(r), gather_output=False).start() for r in range(2)]
+    own = torch.cat([r.finish() for r in runs], 0)
+    assert torch.equal(own, ref)
