@@ -116,8 +116,9 @@ class ProcessGroupComm:
 
 class LocalComm:
     """``world`` emulated ranks inside ONE process on one device (tests): every rank registers its buffer at
-    ``all_gather_block``; ``wait()`` copies the other ranks' blocks in, so all ranks must have ``start()``-ed before any
-    ``finish()``-es - the same ordering a real collective imposes."""
+    ``all_gather_block``; ``wait()`` copies the other ranks' blocks in, so every rank must have issued a gather before any
+    rank waits for it (``GossipShardedRun``: all ``start()``, then all ``finish()``, then all ``result()``) - the
+    ordering a real collective imposes."""
 
     def __init__(self, world: int):
         self.world = world

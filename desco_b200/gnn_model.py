@@ -399,7 +399,8 @@ class GossipShardedRun:
     ``finish()``: for each group, wait for ITS halo only, run layer 1 + post_mp of the own rows (gather + tcgen05 chain
     kernels), and hand the group's output rows to an asynchronous all-gather: the halo of group g+1 and the output of
     group g-1 move over NVLink while group g computes, so only the first halo group and the last output group are exposed.
-    Returns ``out[N, Q]`` (replicated) or, with ``gather_output=False``, the own rows ``[hi - lo, Q]``."""
+    ``result()``: wait for the output all-gathers and return ``out[N, Q]`` (replicated) or, with
+    ``gather_output=False``, the own rows ``[hi - lo, Q]``."""
 
     def __init__(self, model: "GossipBaseGNN", rowptr, col, x, query_emb, comm, query_group: int = 4, gather_output: bool = True):
         from .distributed import gossip_shard_plan
@@ -434,7 +435,7 @@ class GossipShardedRun:
         self.halo_work = [self.comm.all_gather_block(b, plan.n_loc, ("s4", gi)) for gi, b in enumerate(self.s4_groups)]
         return self
 
-    def finish(self) -> torch.Tensor:
+    def finish(self):
         lib, w, dev, plan = self.lib, self.w, self.dev, self.plan
         N, Q = self.N, self.Q
         prec = PRECISION[self.m.precision]
@@ -454,15 +455,19 @@ class GossipShardedRun:
                                                              _ptr(stage), sb, st), "desco_gossip_layer1_group")
                 if self.gather_output:
                     out_work.append(self.comm.all_gather_block(og, plan.n_loc, ("out", q0)))
+        self.out_groups, self.out_work = out_groups, out_work
+        return self
+
+    def result(self) -> torch.Tensor:
         if not self.gather_output:
-            return torch.cat([og[self.lo:self.hi] for og in out_groups], dim=1)
-        for wk in out_work:
+            return torch.cat([og[self.lo:self.hi] for og in self.out_groups], dim=1)
+        for wk in self.out_work:
             wk.wait()
-        return torch.cat([og[:N] for og in out_groups], dim=1)
+        return torch.cat([og[:self.N] for og in self.out_groups], dim=1)
 
 
 def _gossip_forward_sharded(self, rowptr, col, x, query_emb, comm, query_group: int = 4, gather_output: bool = True):
-    return GossipShardedRun(self, rowptr, col, x, query_emb, comm, query_group, gather_output).start().finish()
+    return GossipShardedRun(self, rowptr, col, x, query_emb, comm, query_group, gather_output).start().finish().result()
 
 
 GossipBaseGNN.forward_sharded = _gossip_forward_sharded

@@ -11,7 +11,15 @@
 * ``sage_homog_ref.npz``: the reference's own homogeneous SAGE ``BaseGNN`` (BaseGNNCore.forward + anchor_mlp +
   global_add_pool + post_mp) on the shim, on real canonical neighborhoods (centre marked by node_feature = 1).
 * ``shmp_hetero_ref.npz``: hetero SHMP forward where every leaf module is the reference's own ``SAGEConv`` /
-  ``nn.Linear`` and only the ``to_hetero`` wiring (which cannot be run without PyG) is restated.
+  ``nn.Linear`` and the ``to_hetero`` wiring is restated (kept as a second, independent pin).
+* ``shmp_pipeline_ref.npz``: the reference's OWN pipeline end to end on the extended PyG stand-in
+  (``oracle/ref_shim.install_full``): ``get_neigh_hetero`` -> ``NetworkxToHetero`` -> ``ToTconvHetero``
+  (``transforms.py:180-255,319-412``, imported unmodified) -> collate in batches -> ``BaseGNN.forward`` of
+  ``gnn_model.py`` with ``gnn_core`` converted by the reference's ``to_hetero_old`` (``lightning_model.py:371-421``,
+  executed from source; ``pyg.nn.to_hetero`` = a torch.fx trace of the reference's ``BaseGNNCore.forward`` re-executed
+  per type) -> the reference's ``graph_to_count`` (``lightning_model.py:198-222``).  Also holds the SHMP edge types the
+  reference's ``ToTconvHetero`` assigned, mapped back to the packed edge order.
+* ``partition_*.npz`` edge types (``hetero_d*_edge_tri``) come from the reference's ``ToTconvHetero`` itself as well.
 
 The fixtures travel to the GPU box; ``/root/reference`` does not.
 """
@@ -51,6 +59,59 @@ def kat_graphs():
     return gs
 
 
+def reference_typed_neighborhoods(csr, depth, ref_funcs, tr, centres=None):
+    """``NeighborhoodDataset.process`` + ``__getitem__`` of the reference on the stand-in (``workload.py:243-290``):
+    reference ``get_neigh_hetero`` per node, drop edge-free neighborhoods, reference ``NetworkxToHetero``, pad missing
+    edge types, reference ``ToTconvHetero``.  Returns (packed batch with ``edge_tri`` FROM the reference transform,
+    list of transformed HeteroData in dataset order, per-neighborhood first-count-node info)."""
+    b = P.partition_dataset(csr, depth, mode="hetero", funcs=ref_funcs, with_types=False, centres=centres)
+    get_neigh = ref_funcs["get_neigh_hetero"]
+    datas, first_is_lowest = [], []
+    edge_tri = np.zeros(len(b["edge_col"]), dtype=np.uint8)
+    seen = np.zeros(len(b["edge_col"]), dtype=bool)
+    cache = {}
+    for g, (gid, local) in enumerate(b["index"]):
+        gid, local = int(gid), int(local)
+        if gid not in cache:
+            cache[gid] = csr.to_networkx(gid)
+        neigh = get_neigh(cache[gid], local, depth)
+        order = {"count": [], "canonical": []}
+        for u in neigh.to_directed().nodes:  # NetworkxToHetero assigns per-type ids in this iteration order (:342-348)
+            order[neigh.nodes[u]["type"]].append(u)
+        data = tr.NetworkxToHetero(neigh, type_key="type", feat_key="feat")
+        data.y = torch.empty([1], dtype=torch.double).reshape(1, 1)
+        datas.append((data, order))
+        first_is_lowest.append(order["count"][0] == min(order["count"]))
+    all_types = []
+    for data, _ in datas:  # workload.py:275-282 (a list instead of a set: the order of padded types is immaterial)
+        for et in data.metadata()[1]:
+            if et not in all_types:
+                all_types.append(et)
+    out = []
+    for g, (data, order) in enumerate(datas):
+        for et in all_types:
+            if et not in data.metadata()[1]:
+                data[et].edge_index = torch.empty((2, 0), dtype=torch.long)
+        data = tr.ToTconvHetero()(data)  # the dataset `transform` (main.py:85)
+        lo = int(b["nbh_ptr"][g])
+        base = int(csr.graph_ptr[int(b["index"][g][0])])
+        row_of = {int(b["node_gid"][r]) - base: r for r in range(lo, int(b["nbh_ptr"][g + 1]))}
+        for (s_t, rel, d_t), st in data._edge_store_dict.items():
+            tri = 1 if rel.endswith("_triangle") else 0
+            assert rel.endswith("_triangle") or rel.endswith("_tride")
+            for a, c in st["edge_index"].T.tolist():
+                ru, rv = row_of[order[s_t][a]], row_of[order[d_t][c]]
+                es = np.arange(b["edge_ptr"][rv], b["edge_ptr"][rv + 1])  # packed rows hold INCOMING edges: dst row rv, col = src
+                e = es[b["edge_col"][es] == ru]
+                assert len(e) == 1 and not seen[e[0]]
+                edge_tri[e[0]] = tri
+                seen[e[0]] = True
+        out.append(data)
+    assert seen.all()
+    b["edge_tri"] = edge_tri
+    return b, out, np.asarray(first_is_lowest)
+
+
 def weights_checksum(module) -> float:
     return float(sum(v.double().abs().sum() for v in module.state_dict().values()))
 
@@ -58,7 +119,8 @@ def weights_checksum(module) -> float:
 def main():
     ref_funcs = P.load_reference_functions()
     assert ref_funcs is not None, "run this where /root/reference is mounted"
-    ref = ref_shim.install()
+    ref, tr = ref_shim.install_full()
+    lm = ref_shim.load_lightning_methods()
 
     # ---------------- partition ----------------
     sets = {
@@ -71,8 +133,12 @@ def main():
         out = {"rowptr": csr.rowptr, "col": csr.col, "graph_ptr": csr.graph_ptr}
         for depth in (1, 2, 3, 4):
             for mode in ("hetero", "canonical"):
-                b = P.partition_dataset(csr, depth, mode=mode, funcs=ref_funcs, with_types=False)
-                b["edge_tri"] = type_batch(b)  # literal sparse formulation
+                if mode == "hetero":  # types from the reference's own ToTconvHetero on its own HeteroData
+                    b, _, _ = reference_typed_neighborhoods(csr, depth, ref_funcs, tr)
+                    assert np.array_equal(b["edge_tri"], type_batch(b)), "oracle/shmp_types.py disagrees with the reference"
+                else:  # homogeneous neighborhoods are not typed by the reference pipeline: literal sparse formulation
+                    b = P.partition_dataset(csr, depth, mode=mode, funcs=ref_funcs, with_types=False)
+                    b["edge_tri"] = type_batch(b)
                 for k, v in b.items():
                     out[f"{mode}_d{depth}_{k}"] = v
         np.savez_compressed(os.path.join(HERE, f"partition_{name}.npz"), **out)
@@ -165,6 +231,46 @@ def main():
         count=count.numpy(), seed=31, checksum=weights_checksum(om),
     )
     print("hetero SHMP golden", len(b["centre"]), "neighborhoods, pred range", pred.min().item(), pred.max().item())
+
+    # ---------------- the reference's own pipeline end to end (transforms + to_hetero_old + graph_to_count) ----------------
+    torch.manual_seed(41)
+    om = M.NeighborhoodCountingModel().eval()  # supplies the weights; loaded STRICTLY into the reference modules below,
+    args = M.default_args()                    # which also checks the state-dict key names of SURVEY App. B.3
+    self = SimpleNamespace(
+        emb_model=ref.BaseGNN(1, 64, 64, args, emb_channels=64), emb_model_query=ref.BaseGNN(1, 64, 64, args, emb_channels=64),
+        count_model=torch.nn.Sequential(torch.nn.Linear(128, 256), torch.nn.LeakyReLU(), torch.nn.Linear(256, 1)),
+        kwargs={}, device="cpu")
+    lm["to_hetero_old"](self, tconv_target=True, tconv_query=True)
+    self.emb_model.load_state_dict(om.emb_model.state_dict(), strict=True)
+    self.emb_model_query.load_state_dict(om.emb_model_query.state_dict(), strict=True)
+    self.count_model.load_state_dict(om.count_model.state_dict(), strict=True)
+    self.emb_model.eval(), self.emb_model_query.eval()
+    self.embed_to_count = lambda embs: lm["embed_to_count"](self, embs)
+    queries = [tr.ToTconvHetero()(tr.NetworkxToHetero(nx.graph_atlas(i), type_key="type", feat_key="feat"))
+               for i in M.STANDARD_QUERY_IDS]  # gen_queries, lightning_model.py:37-87 (+ set_queries' DataLoader(batch_size=64))
+    self.query_loader = [ref_shim.Batch.from_data_list(queries)]
+    csr = gen_enzymes_shaped(seed=14, num_graphs=8)  # (seed 13: the first neighborhood, {5, 8}, iterates [8, 5] - the F10 trap)
+    pyg_batch = 64  # several collated batches: the remove_self_loops quirk is evaluated per batch
+    b, datas, first_low = reference_typed_neighborhoods(csr, 4, ref_funcs, tr)
+    store_order = datas[0].metadata()[0]
+    assert store_order == ["count", "canonical"], "first neighborhood iterates its canonical node first (SURVEY F10): pick another seed"
+    for d in datas:  # InMemoryDataset.collate/separate rebuild every element in the FIRST element's store order
+        for t in store_order:
+            d._node_store_dict.move_to_end(t)
+    counts = []
+    with torch.no_grad():
+        for i in range(0, len(datas), pyg_batch):
+            counts.append(lm["graph_to_count"](self, ref_shim.Batch.from_data_list(datas[i:i + pyg_batch])))
+        q_emb = torch.cat([self.emb_model_query(qb_) for qb_ in self.query_loader], 0)
+    counts = torch.cat(counts, 0)
+    np.savez_compressed(
+        os.path.join(HERE, "shmp_pipeline_ref.npz"), rowptr=csr.rowptr, col=csr.col, graph_ptr=csr.graph_ptr,
+        **{f"b_{k}": v for k, v in b.items()}, count=counts.numpy(), query_emb=q_emb.numpy(), seed=41, pyg_batch_size=pyg_batch,
+        checksum=weights_checksum(om), first_count_node_is_lowest_id=first_low,
+        keys=np.array(list(self.emb_model.state_dict().keys())),
+    )
+    print("pipeline golden", len(b["centre"]), "neighborhoods; first count node in networkx order is the lowest id in",
+          int(first_low.sum()), "of", len(first_low), "; count range", counts.min().item(), counts.max().item())
 
 
 if __name__ == "__main__":

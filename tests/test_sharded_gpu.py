@@ -21,6 +21,14 @@ def target(cuda_device):
     return g, g.rowptr.cpu().numpy(), g.col.cpu().numpy()
 
 
+def _rel(a, b):
+    """max |a - b| / max(1, |b|); equal entries (matching infinities of 2^pred on big neighborhoods) count as 0."""
+    a, b = a.double(), b.double()
+    d = (a - b).abs() / b.abs().clamp(min=1.0)
+    d[a == b] = 0.0
+    return d.max().item()
+
+
 def _models(seed):
     from desco_b200.lightning_model import STANDARD_QUERY_IDS, GossipCountingModel, NeighborhoodCountingModel
     from oracle import model as M
@@ -68,7 +76,7 @@ def test_sharded_partition_and_counts_match_oracle_on_centre_sample(target):
         with torch.no_grad():
             counts = pm.graph_to_count(got).cpu()
             want = om.graph_to_count(ref, qb, pyg_batch_size=0)
-        assert ((counts - want).abs() / want.abs().clamp(min=1.0)).max().item() <= 1e-4
+        assert _rel(counts, want) <= 1e-4
 
 
 def test_partition_hub_centre_matches_oracle(target):
@@ -107,7 +115,9 @@ def test_sharded_gossip_matches_oracle_on_node_sample(target, query_group):
     comm = LocalComm(2)
     runs = [GossipShardedRun(pg.emb_model, g.rowptr, g.col, x, qe, comm.for_rank(r), query_group=query_group).start()
             for r in range(2)]
-    outs = [r.finish() for r in runs]
+    for r in runs:
+        r.finish()
+    outs = [r.result() for r in runs]
     assert torch.equal(outs[0], outs[1])
     pg.set_query_emb(qe)
     with torch.no_grad():
@@ -118,8 +128,9 @@ def test_sharded_gossip_matches_oracle_on_node_sample(target, query_group):
     sample = np.concatenate([rng.choice(half, 8, replace=False), half + rng.choice(N_NODES - half, 8, replace=False),
                              [half - 1, half, 0, N_NODES - 1]])
     nodes, ei, pos = gossip_closure(rowptr, col, sample)
-    og.set_query_emb(qe.cpu())
+    og = og.double()  # the literal per-edge index_add over a hub's thousands of neighbours is itself off in fp32
+    og.set_query_emb(qe.cpu().double())
     with torch.no_grad():
-        ref = og.graph_to_count(x[torch.as_tensor(nodes, device="cuda")].cpu(), torch.from_numpy(ei))[torch.as_tensor(pos)]
+        ref = og.graph_to_count(x[torch.as_tensor(nodes, device="cuda")].cpu().double(), torch.from_numpy(ei))[torch.as_tensor(pos)]
     got = outs[0][torch.as_tensor(sample, device="cuda")].cpu()
-    assert ((got - ref).abs() / ref.abs().clamp(min=1.0)).max().item() <= 1e-4
+    assert _rel(got, ref) <= 1e-4

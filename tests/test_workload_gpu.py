@@ -112,10 +112,11 @@ def test_sharded_pipeline_single_rank_equals_direct(cuda_device):
         runs = [GossipShardedRun(pg.emb_model, g.rowptr, g.col, x, qe, comm.for_rank(r), query_group=qg) for r in range(3)]
         for r in runs:
             r.start()
-        outs = [r.finish() for r in runs]
-        for o in outs:
-            assert torch.equal(o, ref)
+        for r in runs:
+            r.finish()
+        for r in runs:
+            assert torch.equal(r.result(), ref)
     comm = LocalComm(2)
     runs = [GossipShardedRun(pg.emb_model, g.rowptr, g.col, x, qe, comm.for_rank(r), gather_output=False).start() for r in range(2)]
-    own = torch.cat([r.finish() for r in runs], 0)
+    own = torch.cat([r.finish().result() for r in runs], 0)
     assert torch.equal(own, ref)
