@@ -101,6 +101,8 @@ SIGNATURES = {
     "desco_shmp_layer_weight_floats": (_L, []),
     "desco_shmp_tc_layer_bytes": (_L, []),
     "desco_shmp_forward": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _L, _I, _VP, _VP]),
+    "desco_shmp_mt_layer_bytes": (_L, []),
+    "desco_shmp_forward_mt": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _L, _I, _VP, _VP]),
     "desco_count_head_workspace_bytes": (_L, [_I, _I]),
     "desco_count_head": (_I, [_VP, _I, _VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _L, _I, _VP, _VP]),
     "desco_gossip_tc_phase_cycles": (_I, [_VP, _I]),

@@ -43,7 +43,7 @@ __global__ void shmp_plan_kernel(const int32_t* __restrict__ nbh_ptr, const int3
     // edge canonical(g) -- first row of g, iff every earlier neighborhood of the PyG batch has exactly two rows.
     const int bs = pyg_batch_size > 0 ? pyg_batch_size : G;
     const int g0 = (g / bs) * bs;
-    if (lo - nbh_ptr[g0] == 2 * (g - g0)) quirk = lo;
+    if (pyg_batch_size >= 0 && lo - nbh_ptr[g0] == 2 * (g - g0)) quirk = lo;  // pyg_batch_size < 0: quirk off
     if (lane == 0) quirk_row[g] = quirk;
   }
   const int canon = hi - 1;
@@ -370,6 +370,7 @@ struct Workspace {
   int32_t* row_nbh; int32_t* crow; uint8_t* canon_code; int32_t* quirk_row;
   float *hA, *hB, *emb_a, *pool, *cvec, *z, *t1, *t2, *t3;
   void* fused;  // tile plan of the fused tcgen05 path
+  void* mt;     // pooling partials of the multi-tile tcgen05 path
   size_t bytes;
 };
 
@@ -392,11 +393,16 @@ Workspace carve(void* base, int V, int G, int layers) {
   w.t2 = (float*)take((size_t)G * F * 4);
   w.t3 = (float*)take((size_t)G * 4 * F * 4);
   w.fused = (void*)take((size_t)desco_internal_shmp_fused_workspace_bytes(G));
+  w.mt = (void*)take((size_t)desco_internal_shmp_mt_workspace_bytes(V, G));
   w.bytes = off;
   return w;
 }
 
 }  // namespace
+
+void desco_internal_shmp_cvec(const float* emb_a, int emb_ld, int layer, const float* Cw, int G, float* cvec, cudaStream_t s) {
+  shmp_cvec_kernel<<<(G + 7) / 8, 256, 0, s>>>(emb_a, emb_ld, layer, Cw, G, cvec);
+}
 
 extern "C" {
 
@@ -406,20 +412,23 @@ int64_t desco_shmp_workspace_bytes(int32_t num_rows, int32_t num_neighborhoods, 
 
 int64_t desco_shmp_layer_weight_floats(void) { return (int64_t)2 * (KC * F + F) + (int64_t)F * 2 * F; }
 int64_t desco_shmp_tc_layer_bytes(void) { return (int64_t)SHMP_TC_LAYER_BYTES; }
+int64_t desco_shmp_mt_layer_bytes(void) { return (int64_t)SHMP_MT_LAYER_BYTES; }
 
-int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
-                       int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
-                       const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
-                       const void* w_layers_tc, const float* w_readout, const void* w_readout_tc, int32_t layers,
-                       int32_t hidden, float* out_emb, void* workspace, int64_t workspace_bytes, int32_t precision,
-                       int32_t* status, void* stream) {
+static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
+                             int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
+                             const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
+                             const void* w_layers_tc, const void* w_layers_mt, const float* w_readout,
+                             const void* w_readout_tc, int32_t layers, int32_t hidden, float* out_emb, void* workspace,
+                             int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream) {
   const int G = num_neighborhoods, V = num_rows;
   if (hidden != F || layers < 1 || input_dim < 1 || G < 0 || V < 0) return DESCO_EINVAL;
   if (precision < DESCO_PRECISION_FP32 || precision > DESCO_PRECISION_BF16) return DESCO_EINVAL;
   if (G == 0) return DESCO_OK;
   if (!nbh_ptr || !edge_ptr || !edge_col || !edge_tri || !w_pre || !w_readout || !out_emb || !workspace) return DESCO_EINVAL;
-  const bool fused = precision != DESCO_PRECISION_FP32;
+  const bool mt = w_layers_mt != nullptr && precision != DESCO_PRECISION_FP32;  // multi-tile tcgen05 path (any size)
+  const bool fused = !mt && precision != DESCO_PRECISION_FP32;
   if (fused && (!hetero || !w_layers_tc || !w_readout_tc || !status)) return DESCO_EINVAL;  // tensor-core path: count/canonical batches
+  if (mt && (!w_layers || !status || (hetero && !w_readout_tc))) return DESCO_EINVAL;
   if (!fused && !w_layers) return DESCO_EINVAL;
   Workspace ws = carve(workspace, V, G, layers);
   if ((int64_t)ws.bytes > workspace_bytes) return DESCO_ENOMEM;
@@ -446,6 +455,13 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
                                                                ws.hA, ws.emb_a, emb_ld);
     DESCO_LAUNCH_CHECK();
   }
+  if (mt) {
+    const int rc = desco_internal_shmp_mt_layers(nbh_ptr, edge_ptr, edge_col, edge_tri, G, V, hetero, ws.row_nbh, ws.crow,
+                                                 ws.canon_code, ws.quirk_row, ws.hA, ws.hB, ws.emb_a, ws.pool, ws.cvec, emb_ld,
+                                                 w_layers, desco_shmp_layer_weight_floats(), w_layers_mt, layers,
+                                                 precision == DESCO_PRECISION_BF16X3 ? 3 : 1, ws.mt, status, s);
+    if (rc) return rc;
+  } else {
   const size_t smem = (size_t)(TM * LDA + KC * F) * sizeof(float) + 3 * TM * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
@@ -482,7 +498,8 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
     shmp_pool_last_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, G, hetero, h_in, layers, ws.pool, emb_ld);
     DESCO_LAUNCH_CHECK();
   }
-  }  // layered fp32 path
+  }  // layer-by-layer FFMA kernels
+  }  // layered paths
 
   // readout: [Wanc (emb_ld x emb_ld) | banc | P0 (emb_ld x F) | b0 | P1 (F x F) | b1 | P2 (F x 4F) | b2 | P3 (4F x F) | b3]
   const float* r = w_readout;
@@ -498,7 +515,7 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
   const float* b3 = r;
   int rc;
   const float* z = ws.pool;
-  if (fused) {  // the same chain on the tensor pipe (csrc/dense_tc.cu); images in w_readout_tc, biases from w_readout
+  if (fused || (mt && hetero)) {  // the same chain on the tensor pipe (csrc/dense_tc.cu); images in w_readout_tc, biases from w_readout
     const int passes = precision == DESCO_PRECISION_BF16X3 ? 6 : 1;  // the readout sums cancel heavily: full 3-way split
     // bf16 hi + mid + lo = 6 bytes per weight; the blob starts with the anchor_mlp images (the post_mp images that follow
     // are for a dense_tc post_mp chain; the default chain below is the single-launch fp32 kernel)
@@ -516,6 +533,29 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
   }
   // post_mp (gnn_model.py:44-53)
   return desco_internal_readout_chain(z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, s);
+}
+
+int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
+                       int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
+                       const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
+                       const void* w_layers_tc, const float* w_readout, const void* w_readout_tc, int32_t layers,
+                       int32_t hidden, float* out_emb, void* workspace, int64_t workspace_bytes, int32_t precision,
+                       int32_t* status, void* stream) {
+  return shmp_forward_impl(nbh_ptr, edge_ptr, edge_col, edge_tri, num_neighborhoods, num_rows, hetero, pyg_batch_size, feat,
+                           input_dim, w_pre, w_layers, w_layers_tc, nullptr, w_readout, w_readout_tc, layers, hidden, out_emb,
+                           workspace, workspace_bytes, precision, status, stream);
+}
+
+int desco_shmp_forward_mt(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
+                          int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
+                          const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
+                          const void* w_layers_mt, const float* w_readout, const void* w_readout_tc, int32_t layers,
+                          int32_t hidden, float* out_emb, void* workspace, int64_t workspace_bytes, int32_t precision,
+                          int32_t* status, void* stream) {
+  if (!w_layers_mt || precision == DESCO_PRECISION_FP32) return DESCO_EINVAL;
+  return shmp_forward_impl(nbh_ptr, edge_ptr, edge_col, edge_tri, num_neighborhoods, num_rows, hetero, pyg_batch_size, feat,
+                           input_dim, w_pre, w_layers, nullptr, w_layers_mt, w_readout, w_readout_tc, layers, hidden, out_emb,
+                           workspace, workspace_bytes, precision, status, stream);
 }
 
 int64_t desco_count_head_workspace_bytes(int32_t num_neighborhoods, int32_t num_queries) {

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         const int bs = p.pyg_batch_size > 0 ? p.pyg_batch_size : p.G;
         const int g0 = (g / bs) * bs;
         const int lo = p.nbh_ptr[g];
-        sQuirk[tid] = (lo - p.nbh_ptr[g0] == 2 * (g - g0)) ? (lo - row0) : -1;
+        sQuirk[tid] = (p.pyg_batch_size >= 0 && lo - p.nbh_ptr[g0] == 2 * (g - g0)) ? (lo - row0) : -1;  // < 0: quirk off
       }
       for (int r = tid; r <= R; r += THREADS) sEptr[r] = p.edge_ptr[row0 + r] - e0;
       if (edges_staged)

@@ -35,3 +35,17 @@ int desco_internal_readout_chain(const float* Z, int ldz, int K0, int G, const f
 int desco_internal_count_head_fused(const float* emb_t, int G, const float* emb_q, int Q, const float* W1a, const float* W1b,
                                     const float* b1, const float* w2, const float* b2, float* pred, float* count,
                                     cudaStream_t s);
+
+/* bytes of one layer in the multi-tile weight blob (csrc/shmp_mt.cu): 3 K blocks x [hi | lo] images of a [64 n x 64 k]
+ * block of Wc^T (tcpack.pack_b_operand) */
+#define SHMP_MT_LAYER_BYTES (3 * 2 * 64 * 128)
+
+int64_t desco_internal_shmp_mt_workspace_bytes(int num_rows, int num_neighborhoods);
+int desco_internal_shmp_mt_layers(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col,
+                                  const uint8_t* edge_tri, int G, int V, int hetero, const int32_t* row_nbh,
+                                  const int32_t* crow, const uint8_t* canon_code, const int32_t* quirk_row, float* hA,
+                                  float* hB, float* emb_a, float* pool, float* cvec, int emb_ld, const float* w_layers,
+                                  int64_t layer_floats, const void* w_layers_mt, int layers, int passes, void* workspace,
+                                  int32_t* status, cudaStream_t s);
+// cvec[g] = h_canonical^l[g] . Cw^l (shmp.cu)
+void desco_internal_shmp_cvec(const float* emb_a, int emb_ld, int layer, const float* Cw, int G, float* cvec, cudaStream_t s);

@@ -50,7 +50,7 @@ __global__ void train_plan_kernel(const int32_t* __restrict__ nbh_ptr, int G, in
     if (hetero) {  // gnn_model.py:389-390 applied to the bipartite relations: see shmp.cu shmp_plan_kernel
       const int bs = pyg_batch_size > 0 ? pyg_batch_size : G;
       const int g0 = (g / bs) * bs;
-      if (lo - nbh_ptr[g0] == 2 * (g - g0)) quirk = lo;
+      if (pyg_batch_size >= 0 && lo - nbh_ptr[g0] == 2 * (g - g0)) quirk = lo;  // pyg_batch_size < 0: quirk off
     }
     quirk_row[g] = quirk;
   }

@@ -146,6 +146,7 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
         pre += [d(lin.weight).t().contiguous().flatten(), d(lin.bias)]
     layers = []
     tc_layers = []
+    mt_layers = []
     for l in range(core.layer_num):
         def fused(dst, rels):
             U, u = d(core.updates[l][dst].weight), d(core.updates[l][dst].bias)
@@ -174,6 +175,8 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
             Wa = torch.zeros(3 * F, F, dtype=torch.float64)
             bias_a = torch.zeros(F, dtype=torch.float64)
         layers += [Wc.contiguous().flatten(), bias_c, Cw.contiguous().flatten(), Wa.contiguous().flatten(), bias_a]
+        WcT = Wc.t()  # multi-tile form (csrc/shmp_mt.cu): per K block (tri | tride | self) the [64 n][64 k] block of Wc^T
+        mt_layers += [pack_b_operand(WcT[:, kb * F:(kb + 1) * F]) for kb in range(3)]
         if hetero:  # tensor-core form (csrc/shmp_fused.cu): B operand rows n = output column, k contiguous
             B = torch.cat([Wc[0:F].t(), Wc[F:2 * F].t(), Wc[2 * F:3 * F].t()], 0)  # [192][64]
             f32b = lambda t: t.to(torch.float32).contiguous().view(torch.uint8).reshape(-1)
@@ -182,7 +185,8 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
     for i in (0, 3, 5, 7):
         ro += [d(base.post_mp[i].weight).t().contiguous().flatten(), d(base.post_mp[i].bias)]
     f32 = lambda parts: torch.cat(parts).to(torch.float32).to(dev).contiguous()
-    out = {"pre": f32(pre), "layers": f32(layers), "readout": f32(ro)}
+    out = {"pre": f32(pre), "layers": f32(layers), "readout": f32(ro), "layers_mt": torch.cat(mt_layers).to(dev).contiguous()}
+    assert out["layers_mt"].numel() == core.layer_num * _lib.load().desco_shmp_mt_layer_bytes()
     if tc_layers:
         out["readout_tc"] = torch.cat([pack_dense_tc(d(base.anchor_mlp[0].weight), 144), pack_dense_tc(d(base.post_mp[0].weight), 64),
                                        pack_dense_tc(d(base.post_mp[3].weight), 64), pack_dense_tc(d(base.post_mp[5].weight), 128),
@@ -210,6 +214,7 @@ class BaseGNN(_PackedWeightsMixin, nn.Module):
             nn.ReLU(), nn.Linear(hidden_dim, 256), nn.ReLU(), nn.Linear(256, output_dim),
         )
         self.precision = "bf16x3"  # tcgen05 path, ~3e-6 from the fp32 oracle; "fp32" = layer-by-layer FFMA kernels
+        self.force_multi_tile = False  # tests: send small neighborhoods through the multi-tile tcgen05 kernels too
         self.pyg_batch_size = 0  # 0: the whole NeighborhoodBatch is one collated PyG batch
         self._init_cache()
 
@@ -239,18 +244,23 @@ class BaseGNN(_PackedWeightsMixin, nn.Module):
         if feat is not None:
             feat = feat.to(device=dev, dtype=torch.float32).contiguous()
             assert feat.shape == (V, core.input_dim)
-        # the tensor-core precisions keep a whole neighborhood inside one 128-row tile; query graphs (single node type)
-        # and batches that may hold larger neighborhoods take the layer-by-layer fp32 kernels
+        # tensor-core precisions: batches whose neighborhoods all fit a 128-row tile take the fused kernel (features never
+        # leave the chip); anything larger takes the multi-tile kernels (features in HBM between layers, any size);
+        # query graphs (single node type, a few dozen rows, embeddings cached) stay on the fp32 kernels
         precision = PRECISION[self.precision]
-        if not hetero or data.max_rows > TILE_ROWS:
+        if not hetero and not self.force_multi_tile:
             precision = 0
+        multi_tile = precision != 0 and (self.force_multi_tile or not hetero or data.max_rows > TILE_ROWS)
         status = torch.zeros(1, dtype=torch.int32, device=dev) if precision else None
         with torch.cuda.device(dev):
-            _lib.check(lib.desco_shmp_forward(
-                _ptr(data.nbh_ptr), _ptr(data.edge_ptr), _ptr(data.edge_col), _ptr(data.edge_tri), G, V, int(hetero),
-                int(self.pyg_batch_size), _ptr(feat), core.input_dim, _ptr(w["pre"]), _ptr(w["layers"]),
-                _ptr(w.get("layers_tc")), _ptr(w["readout"]), _ptr(w.get("readout_tc")), core.layer_num, core.hidden_dim,
-                _ptr(out), _ptr(work), wbytes, precision, _ptr(status), _stream()), "desco_shmp_forward")
+            common = (_ptr(data.nbh_ptr), _ptr(data.edge_ptr), _ptr(data.edge_col), _ptr(data.edge_tri), G, V, int(hetero),
+                      int(self.pyg_batch_size), _ptr(feat), core.input_dim, _ptr(w["pre"]), _ptr(w["layers"]))
+            tail = (_ptr(w["readout"]), _ptr(w.get("readout_tc")), core.layer_num, core.hidden_dim, _ptr(out), _ptr(work),
+                    wbytes, precision, _ptr(status), _stream())
+            if multi_tile:
+                _lib.check(lib.desco_shmp_forward_mt(*common, _ptr(w["layers_mt"]), *tail), "desco_shmp_forward_mt")
+            else:
+                _lib.check(lib.desco_shmp_forward(*common, _ptr(w.get("layers_tc")), *tail), "desco_shmp_forward")
         if status is not None:
             self.last_status = status  # device int32; 0 = ok.  Checked lazily (check_status) to keep the launch async.
         return out

@@ -130,7 +130,8 @@ class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
 
     def set_pyg_batch_size(self, n: int):
         """Size of the collated batches the reference would form (``config.py:255``); only affects which bipartite
-        edges SAGEConv's remove_self_loops drops (see gnn_model / DESIGN.md)."""
+        edges SAGEConv's remove_self_loops drops (see gnn_model / DESIGN.md).  0: the whole input is one batch;
+        negative: do not reproduce the quirk at all (no edge is dropped)."""
         self.emb_model.pyg_batch_size = int(n)
         return self
 

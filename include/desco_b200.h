@@ -147,8 +147,11 @@ int desco_shmp_edge_types(const int32_t* edge_ptr, const int32_t* edge_col, int3
  * Input: a packed batch (see desco_partition_fill).  hetero = 1: target neighborhoods (node types count/canonical,
  * canonical = last row of each neighborhood, 6 relations); hetero = 0: query graphs (one node type, 2 relations, no
  * anchor_mlp).  pyg_batch_size: size of the collated PyG batches the reference would have formed (config.py:255,
- * default 512; 0 = the whole input is one batch) - needed only to reproduce SAGEConv's remove_self_loops on the
- * bipartite relations (gnn_model.py:389-390), see DESIGN.md "reference quirks".
+ * default 512; 0 = the whole input is one batch; < 0 = do not reproduce the quirk) - needed only to reproduce
+ * SAGEConv's remove_self_loops on the bipartite relations (gnn_model.py:389-390), see DESIGN.md "reference quirks":
+ * the dropped edge joins the canonical node and the FIRST count node of the neighborhood, which here is the lowest
+ * node id; in the reference it is the first count node in networkx iteration order, which is the lowest id in most but
+ * not all neighborhoods (225 of 232 in tests/golden/shmp_pipeline_ref.npz) and is not a function of the graph alone.
  * feat: [num_rows, input_dim] node features or NULL for ZeroNodeFeat (workload.py:431-440).
  *
  * Weight blobs (float32, K-major = transposed nn.Linear weights; built by desco_b200.gnn_model.pack_*):
@@ -185,6 +188,22 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
                        const void* w_layers_tc, const float* w_readout, const void* w_readout_tc, int32_t layers,
                        int32_t hidden, float* out_emb, void* workspace, int64_t workspace_bytes, int32_t precision,
                        int32_t* status, void* stream);
+
+/* The same forward for neighborhoods of ANY size on the tensor cores (csrc/shmp_mt.cu): features stay in HBM between
+ * layers, a tile is 128 consecutive count rows whatever neighborhoods they belong to, the edge-type-split gather writes
+ * the [128 x 192] operand into shared memory as bf16 hi/lo images and the product runs on tcgen05.  Serves Syn_1827-shaped
+ * batches (neighborhoods of several hundred rows), the depth-2 balls of a power-law target (10^3 - 10^6 rows) and query
+ * graphs (hetero = 0).  w_layers (fp32 blob, required: biases, Cw, Wa are read from it) as above; w_layers_mt: per layer
+ * desco_shmp_mt_layer_bytes() bytes = for each 64-wide K block (tri | tride | self) the [64 n][64 k] block of Wc^T as a
+ * bf16 hi / lo pre-swizzled operand image (desco_b200.tcpack.pack_b_operand).  precision: BF16X3 or BF16.
+ * w_readout_tc is required for hetero batches. */
+int64_t desco_shmp_mt_layer_bytes(void);
+int desco_shmp_forward_mt(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
+                          int32_t num_neighborhoods, int32_t num_rows, int32_t hetero, int32_t pyg_batch_size,
+                          const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
+                          const void* w_layers_mt, const float* w_readout, const void* w_readout_tc, int32_t layers,
+                          int32_t hidden, float* out_emb, void* workspace, int64_t workspace_bytes, int32_t precision,
+                          int32_t* status, void* stream);
 
 /* Query-conditioned count head.  Replaces embed_to_count / the per-query loop of graph_to_count
  * (lightning_model.py:176-222, count_model :127-131):  pred[g,q] = count_model(cat(emb_target[g], emb_query[q])),

@@ -172,3 +172,25 @@ def test_large_graph_views_agree_with_the_whole_graph_oracle():
         ref = og.graph_to_count(x, torch.from_numpy(csr.edge_index()))[torch.as_tensor(sample)]
         got = og.graph_to_count(x[torch.as_tensor(nodes)], torch.from_numpy(ei))[torch.as_tensor(pos)]
     assert (ref - got).abs().max().item() <= 1e-5
+
+
+def test_oracle_matches_the_reference_pipeline_golden(golden_dir):
+    """shmp_pipeline_ref.npz was produced by the reference's own get_neigh_hetero -> NetworkxToHetero -> ToTconvHetero ->
+    collate -> to_hetero_old'd BaseGNN -> graph_to_count on the PyG stand-in (tests/golden/make_golden.py): pins the
+    to_hetero wiring, the SHMP typing and the remove_self_loops quirk of oracle/model.py + oracle/shmp_types.py."""
+    z = np.load(os.path.join(golden_dir, "shmp_pipeline_ref.npz"))
+    b = {k[2:]: z[k] for k in z.files if k.startswith("b_")}
+    assert np.array_equal(type_batch(b), b["edge_tri"])  # the reference's ToTconvHetero == the literal formulation
+    torch.manual_seed(int(z["seed"]))
+    om = M.NeighborhoodCountingModel().eval()
+    assert abs(sum(float(v.double().abs().sum()) for v in om.state_dict().values()) - float(z["checksum"])) < 1e-6 * float(z["checksum"])
+    qb = M.query_batch()
+    with torch.no_grad():
+        c = om.graph_to_count(b, qb, pyg_batch_size=int(z["pyg_batch_size"]))
+        qe = om.get_query_emb(qb)
+        c_off = om.graph_to_count(b, qb, pyg_batch_size=int(z["pyg_batch_size"]), self_loop_quirk=False)
+    assert (qe - torch.from_numpy(z["query_emb"])).abs().max().item() <= 1e-6
+    assert (c - torch.from_numpy(z["count"])).abs().max().item() <= 1e-6
+    assert (c_off - torch.from_numpy(z["count"])).abs().max().item() > 1e-5  # the fixture does exercise the quirk
+    # state-dict keys of the reference's hetero modules (PyG to_hetero naming) == the oracle's == the product's
+    assert sorted(z["keys"].tolist()) == sorted(om.emb_model.state_dict().keys())

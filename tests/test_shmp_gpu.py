@@ -31,7 +31,7 @@ def _models(seed=0, bias_shift=None):
     return om, pm
 
 
-def _check(om, pm, b_np, pyg_bs=None, tol=TOL, precision="bf16x3"):
+def _check(om, pm, b_np, pyg_bs=None, tol=TOL, precision="bf16x3", multi_tile=False):
     from desco_b200.data import NeighborhoodBatch
     from oracle import model as M
 
@@ -41,9 +41,11 @@ def _check(om, pm, b_np, pyg_bs=None, tol=TOL, precision="bf16x3"):
     batch = NeighborhoodBatch.from_numpy(b_np)
     pm.set_pyg_batch_size(pyg_bs or 0)
     pm.set_precision(precision)
+    pm.emb_model.force_multi_tile = multi_tile
     with torch.no_grad():
         count, pred = pm.embed_to_count((pm.emb_model(batch), pm.get_query_emb()), want_pred=True)
     torch.cuda.synchronize()
+    pm.emb_model.force_multi_tile = False
     pm.emb_model.check_status()
     # random-init weights push pred of big (Syn-shaped, 300-node) neighborhoods to ~500, where the fp32 oracle itself is
     # 6e-4 away from an fp64 run: the pre-exponent check is relative above 1, and counts (2**pred, overflowing fp32
@@ -88,6 +90,39 @@ def test_shmp_matches_reference_leaf_golden(cuda_device, golden_dir):
     assert (count - torch.from_numpy(z["count"])).abs().max().item() <= TOL
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_pipeline_matches_the_reference_pipeline_golden(cuda_device, golden_dir, precision):
+    """shmp_pipeline_ref.npz = the reference's OWN get_neigh_hetero -> NetworkxToHetero -> ToTconvHetero -> collate (64 per
+    batch) -> to_hetero_old'd BaseGNN.forward -> graph_to_count, run on the PyG stand-in (tests/golden/make_golden.py).
+    The product pipeline (partition + typing kernels, fused SHMP, count head) must reproduce it from the CSR alone."""
+    from desco_b200.data import DeviceCSR, partition_batch
+    from desco_b200.graph import TargetCSR
+    from desco_b200.lightning_model import NeighborhoodCountingModel, STANDARD_QUERY_IDS
+    from oracle import model as M
+
+    z = np.load(os.path.join(golden_dir, "shmp_pipeline_ref.npz"))
+    torch.manual_seed(int(z["seed"]))
+    om = M.NeighborhoodCountingModel().eval()
+    pm = NeighborhoodCountingModel().eval()
+    pm.load_state_dict(om.state_dict())
+    pm = pm.cuda()
+    pm.set_queries(STANDARD_QUERY_IDS)
+    pm.set_pyg_batch_size(int(z["pyg_batch_size"]))
+    pm.set_precision(precision)
+    batch = partition_batch(DeviceCSR.from_host(TargetCSR(z["rowptr"], z["col"], z["graph_ptr"])), None, 4, "hetero")
+    got = batch.to_numpy()
+    for k in ("nbh_ptr", "node_gid", "edge_ptr", "edge_col", "edge_tri", "centre", "indicator", "index"):
+        assert np.array_equal(got[k], z["b_" + k]), k  # edge_tri: what the reference's ToTconvHetero assigned
+    with torch.no_grad():
+        count = pm.graph_to_count(batch).cpu()
+    assert (pm.get_query_emb().cpu() - torch.from_numpy(z["query_emb"])).abs().max().item() <= TOL
+    assert (count - torch.from_numpy(z["count"])).abs().max().item() <= TOL
+    pm.set_pyg_batch_size(-1)  # the quirk knob: off -> no bipartite edge is dropped, and the fixture notices
+    with torch.no_grad():
+        off = pm.graph_to_count(batch).cpu()
+    assert 1e-5 < (off - torch.from_numpy(z["count"])).abs().max().item() < 1e-2
+
+
 @pytest.mark.parametrize("gen,kw", [(gen_mutag_shaped, dict(num_graphs=40)), (gen_cox2_shaped, dict(num_graphs=30)),
                                     (gen_enzymes_shaped, dict(num_graphs=40)), (gen_imdb_shaped, dict(num_graphs=30)),
                                     (gen_syn1827_shaped, dict(stride=200))])
@@ -100,6 +135,55 @@ def test_shmp_counts_match_oracle(cuda_device, gen, kw):
     b = P.partition_dataset(gen(seed=4, **kw), 4)
     _check(om, pm, b, precision="bf16x3")
     _check(om, pm, b, precision="fp32")
+
+
+@pytest.mark.parametrize("gen,kw", [(gen_mutag_shaped, dict(num_graphs=40)), (gen_enzymes_shaped, dict(num_graphs=40)),
+                                    (gen_imdb_shaped, dict(num_graphs=30)), (gen_syn1827_shaped, dict(stride=200))])
+def test_multi_tile_tensor_core_path_matches_oracle(cuda_device, gen, kw):
+    """csrc/shmp_mt.cu (features in HBM between layers, 128-row tiles across neighborhood boundaries, tcgen05 product):
+    the path of neighborhoods beyond one tile (Syn-shaped: up to ~700 rows), forced here onto the small-neighborhood
+    datasets as well.  Same 1e-4 bar; the result must also be run-to-run deterministic (no atomics in the pooling)."""
+    from desco_b200.data import NeighborhoodBatch
+    from oracle import partition as P
+
+    om, pm = _models(1)
+    b = P.partition_dataset(gen(seed=4, **kw), 4)
+    _check(om, pm, b, precision="bf16x3", multi_tile=True)
+    _check(om, pm, b, pyg_bs=64, precision="bf16x3", multi_tile=True)
+    pm.emb_model.force_multi_tile = True
+    batch = NeighborhoodBatch.from_numpy(b)
+    with torch.no_grad():
+        a1, a2 = pm.emb_model(batch).clone(), pm.emb_model(batch).clone()
+    pm.emb_model.force_multi_tile = False
+    assert torch.equal(a1, a2)
+
+
+def test_multi_tile_path_hub_rows_and_query_graphs(cuda_device):
+    """A star-heavy target (count rows with thousands of in-neighborhood edges: the whole-CTA hub gather) and the query
+    graphs (single node type) through the multi-tile kernels."""
+    import networkx as nx
+
+    from desco_b200.graph import csr_from_networkx
+    from oracle import model as M
+    from oracle import partition as P
+
+    om, pm = _models(3)
+    n = 3000
+    g = nx.gnm_random_graph(n, 6000, seed=5)
+    g.add_edges_from((0, v) for v in range(1, n))  # node 0: a count row with ~3000 in-neighborhood edges
+    g.add_edges_from((7, v) for v in range(8, n, 2))
+    csr = csr_from_networkx([g])
+    centres = np.array([n - 1, n - 2, 1500])
+    b = P.partition_dataset(csr, 2, centres=centres)
+    assert np.diff(b["edge_ptr"]).max() > 2048  # a hub row
+    _check(om, pm, b, precision="bf16x3")
+    pm.emb_model_query.force_multi_tile = True
+    pm.emb_model_query.precision = "bf16x3"
+    pm._invalidate_caches()
+    with torch.no_grad():
+        ref = om.get_query_emb(M.query_batch())
+        got = pm.get_query_emb().cpu()
+    assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
 
 
 def test_shmp_bf16_single_pass_variant(cuda_device):
