@@ -544,9 +544,15 @@ def config5_parity(ctx, args, g, nm, gm, pipe, x, qe, out, depth):
     om = M.NeighborhoodCountingModel().eval()
     om.load_state_dict({k: v.cpu() for k, v in nm.state_dict().items()})
     with torch.no_grad():
-        want = om.graph_to_count(ref, M.query_batch(), pyg_batch_size=512)
+        want_pred = om.pre_exponent(ref, M.query_batch(), pyg_batch_size=512)
+        want = 2 ** want_pred - 1
         have = nm.graph_to_count(got).cpu()
-    count_err = _rel_err(have, want) if want.numel() else 0.0
+        have_pred = nm.graph_to_pred(got).cpu()
+    # 2^pred magnifies a relative pre-exponent error by ln2 * |pred| (random-init weights push pred of these 10^3-row
+    # neighborhoods to ~20): the bar is on the pre-exponent, and on the counts where |pred| <= 8 (tests/test_shmp_gpu.py)
+    sane = want_pred.abs() <= 8.0
+    pred_err = _rel_err(have_pred, want_pred) if want.numel() else 0.0
+    count_err = _rel_err(have[sane], want[sane]) if bool(sane.any()) else 0.0
     # the gossip oracle runs in float64: its literal per-edge index_add accumulates a hub's 10^4 neighbour rows
     # sequentially, which in fp32 is itself off by more than the tolerance
     og = M.GossipCountingModel()
@@ -561,12 +567,13 @@ def config5_parity(ctx, args, g, nm, gm, pipe, x, qe, out, depth):
     res = {
         "oracle": "CPU restatement (oracle/) on the k-hop balls / 2-hop closure of the samples (oracle/large.py); gossip oracle in float64",
         "partition_sample_centres": int(len(centres)), "partition_and_types_bit_exact": bool(part_ok),
-        "count_sample_neighborhoods": int(want.shape[0]), "count_max_err_floor1": count_err,
+        "count_sample_neighborhoods": int(want.shape[0]), "pre_exponent_max_err_floor1": pred_err,
+        "count_max_err_floor1_where_abs_pred_le_8": count_err,
         "gossip_sample_nodes": int(len(nodes_s)), "gossip_closure_nodes": int(len(nodes)), "gossip_max_err_floor1": gerr,
         "tolerance": TOL,
     }
     assert part_ok, "config-5 partition sample differs from the oracle"
-    assert count_err <= TOL and gerr <= TOL, res
+    assert pred_err <= TOL and count_err <= TOL and gerr <= TOL, res
     return res
 
 

@@ -115,6 +115,8 @@ SIGNATURES = {
     "desco_gossip_layer0_grouped": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _I, _L, _VP]),
     "desco_gossip_layer1_group": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _I, _I, _VP, _L, _VP]),
     "desco_gossip_layer1_workspace_bytes": (_L, [_I, _I, _I]),
+    "desco_spmm_sum": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _VP, _I, _VP]),
+    "desco_gossip_gate": (_I, [_VP, _I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
     "desco_shmp_fused_phase_cycles": (_I, [_VP, _I]),
     "desco_train_plan": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "desco_train_aggregate": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP, _I, _VP, _I, _VP, _I, _VP, _I, _VP]),

@@ -92,9 +92,45 @@ class _PackedWeightsMixin:
         return hit[2]
 
 
+def _csr_by_target(edge_index: torch.Tensor, n_dst: int, extra: Optional[torch.Tensor] = None):
+    """edge_index [2, E] (source, target) -> (rowptr[n_dst + 1], col[E] = sources, extra permuted alike), int32, on the
+    edges' device.  Index plumbing only (sort + bincount); the arithmetic runs in csrc/conv.cu."""
+    src, dst = edge_index[0].long(), edge_index[1].long()
+    order = torch.argsort(dst, stable=True)
+    rowptr = torch.zeros(n_dst + 1, dtype=torch.int64, device=edge_index.device)
+    rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n_dst), 0)
+    return rowptr.to(torch.int32), src[order].to(torch.int32).contiguous(), (None if extra is None else extra[order].contiguous())
+
+
+def _spmm_sum(rowptr, col, edge_w, x: torch.Tensor, n_dst: int) -> torch.Tensor:
+    lib = _lib.load()
+    x = x.to(torch.float32).contiguous()
+    out = torch.empty((n_dst, x.shape[1]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.desco_spmm_sum(_ptr(rowptr), _ptr(col), _ptr(edge_w), n_dst, _ptr(x), x.stride(0), x.shape[1], _ptr(out),
+                                      out.stride(0), _stream()), "desco_spmm_sum")
+    return out
+
+
+def _linear(xs: List[torch.Tensor], ws: List[torch.Tensor], bias: torch.Tensor) -> torch.Tensor:
+    """sum_i xs[i] . ws[i]^T + bias through ``desco_train_dense`` (64-wide K blocks, output width a multiple of 64)."""
+    from .training import _Ops
+
+    n = ws[0].shape[0]
+    if n % 64 or any(x.shape[1] % 64 for x in xs):
+        raise NotImplementedError("the CUDA dense primitive needs channel counts that are multiples of 64")
+    y = torch.empty((xs[0].shape[0], n), dtype=torch.float32, device=xs[0].device)
+    if y.shape[0]:
+        with torch.cuda.device(y.device):
+            _Ops().dense([x.contiguous() for x in xs], [w.detach() for w in ws], [bias.detach()], y)
+    return y
+
+
 class SAGEConv(nn.Module):
-    """``gnn_model.py:362-404``: ``lin(sum_{j->i} x_j)``.  Parameter holder; the arithmetic runs fused inside
-    ``BaseGNN.forward`` (csrc/shmp.cu), one launch per layer for all relations."""
+    """``gnn_model.py:362-404``: ``lin(sum_{j->i} x_j)``.  Inside ``BaseGNN.forward`` the arithmetic runs fused for all
+    relations and layers (csrc/shmp_fused.cu, shmp_mt.cu); called on its own it is ``forward(x | (x_src, x_dst),
+    edge_index)`` of the reference on CUDA tensors: ``remove_self_loops`` (:389-390), sum-aggregation at the targets
+    (csrc/conv.cu), then ``lin`` (csrc/train.cu dense).  Inference only (no autograd through the raw launches)."""
 
     def __init__(self, in_channels, out_channels, aggr="add", **kwargs):
         super().__init__()
@@ -104,6 +140,18 @@ class SAGEConv(nn.Module):
 
     def reset_parameters(self):
         self.lin.reset_parameters()
+
+    def forward(self, x, edge_index, edge_weight=None, size=None, res_n_id=None):
+        x_src, x_dst = (x, x) if isinstance(x, torch.Tensor) else x
+        if not x_src.is_cuda:
+            raise RuntimeError("desco_b200 modules run on CUDA tensors only (no CPU fallback)")
+        n_dst = x_dst.shape[0] if size is None else size[1]
+        if edge_index is None:
+            edge_index = torch.zeros((2, 0), dtype=torch.long, device=x_src.device)
+        if edge_index.numel():
+            edge_index = edge_index[:, edge_index[0] != edge_index[1]]  # pyg_utils.remove_self_loops
+        rowptr, col, _ = _csr_by_target(edge_index, n_dst)
+        return _linear([_spmm_sum(rowptr, col, None, x_src, n_dst)], [self.lin.weight], self.lin.bias)
 
     def __repr__(self):
         return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)
@@ -226,6 +274,8 @@ class BaseGNN(_PackedWeightsMixin, nn.Module):
             from .transforms import as_neighborhood_batch
 
             data = as_neighborhood_batch(data)
+        if feat is None:
+            feat = data._cache.get("feat")  # non-zero node features of a PyG-shaped input
         lib = _lib.load()
         core = self.gnn_core
         hetero = "canonical" in core.meta[0]
@@ -253,8 +303,10 @@ class BaseGNN(_PackedWeightsMixin, nn.Module):
         multi_tile = precision != 0 and (self.force_multi_tile or not hetero or data.max_rows > TILE_ROWS)
         status = torch.zeros(1, dtype=torch.int32, device=dev) if precision else None
         with torch.cuda.device(dev):
+            # PyG-shaped input IS one collated batch: the remove_self_loops quirk is evaluated over it as a whole
+            pyg_bs = int(self.pyg_batch_size) if not data._cache.get("pyg_collated") else min(int(self.pyg_batch_size), 0)
             common = (_ptr(data.nbh_ptr), _ptr(data.edge_ptr), _ptr(data.edge_col), _ptr(data.edge_tri), G, V, int(hetero),
-                      int(self.pyg_batch_size), _ptr(feat), core.input_dim, _ptr(w["pre"]), _ptr(w["layers"]))
+                      pyg_bs, _ptr(feat), core.input_dim, _ptr(w["pre"]), _ptr(w["layers"]))
             tail = (_ptr(w["readout"]), _ptr(w.get("readout_tc")), core.layer_num, core.hidden_dim, _ptr(out), _ptr(work),
                     wbytes, precision, _ptr(status), _stream())
             if multi_tile:
@@ -278,7 +330,10 @@ class BaseGNN(_PackedWeightsMixin, nn.Module):
 
 
 class GossipConv(nn.Module):
-    """``gnn_model.py:280-359`` parameter holder (lin_com, lin_update, lin_gate); arithmetic in csrc/gossip.cu."""
+    """``gnn_model.py:280-359``.  Inside ``GossipBaseGNN`` both layers, all queries and post_mp run fused (csrc/gossip.cu);
+    called on its own it is the reference's ``forward(x, edge_index, edge_weight, query_emb)`` on CUDA tensors:
+    ``lin_com`` per NODE (the reference applies it per edge, :341 - same sums), messages scaled by the gate or 1 - gate by
+    edge direction (:342-343), summed at the targets, ``lin_update(cat(aggr, x))`` (:347-348).  Inference only."""
 
     def __init__(self, in_channels, out_channels, emb_channels, aggr="add", **kwargs):
         super().__init__()
@@ -292,6 +347,41 @@ class GossipConv(nn.Module):
 
     def __repr__(self):
         return "{}({}, {})".format(self.__class__.__name__, self.in_channels, self.out_channels)
+
+    def _gate_value(self, query_emb: torch.Tensor) -> torch.Tensor:
+        """``gnn_model.py:353-356``: ``lin_gate(query_emb)`` -> [Q, 1]."""
+        lib = _lib.load()
+        qe = query_emb.to(torch.float32).contiguous()
+        if not qe.is_cuda:
+            raise RuntimeError("desco_b200 modules run on CUDA tensors only (no CPU fallback)")
+        l1, l2 = self.lin_gate[0], self.lin_gate[2]
+        gate = torch.empty((qe.shape[0], 1), dtype=torch.float32, device=qe.device)
+        with torch.cuda.device(qe.device):
+            _lib.check(lib.desco_gossip_gate(_ptr(qe), qe.shape[0], qe.shape[1], _ptr(l1.weight.detach().contiguous()),
+                                             _ptr(l1.bias.detach()), l1.weight.shape[0], _ptr(l2.weight.detach().contiguous()),
+                                             _ptr(l2.bias.detach()), _ptr(gate), _stream()), "desco_gossip_gate")
+        return gate
+
+    def forward(self, x, edge_index, edge_weight=None, size=None, res_n_id=None, query_emb=None):
+        if not x.is_cuda:
+            raise RuntimeError("desco_b200 modules run on CUDA tensors only (no CPU fallback)")
+        n = x.shape[0]
+        edge_index = edge_index[:, edge_index[0] != edge_index[1]] if edge_weight is None else edge_index
+        if edge_weight is None:  # :316-321: symmetrise + coalesce, direction flag = source < target
+            key = torch.unique(torch.cat([edge_index[0] * n + edge_index[1], edge_index[1] * n + edge_index[0]]))
+            edge_index = torch.stack([key // n, key % n])
+            edge_weight = edge_index[0] < edge_index[1]
+        else:
+            keep = edge_index[0] != edge_index[1]
+            edge_index, edge_weight = edge_index[:, keep], edge_weight[keep]
+        gate = self._gate_value(query_emb).view(-1)[0] if query_emb is not None else torch.tensor(0.5, device=x.device)
+        w = torch.where(edge_weight.bool(), gate, 1.0 - gate).to(torch.float32)
+        rowptr, col, w = _csr_by_target(edge_index, n, w)
+        y = _linear([x.to(torch.float32)], [self.lin_com.weight], self.lin_com.bias)  # lin_com(x_j), once per node
+        aggr = _spmm_sum(rowptr, col, w, y, n)
+        oc = self.out_channels
+        return _linear([aggr, x.to(torch.float32)], [self.lin_update.weight[:, :oc], self.lin_update.weight[:, oc:]],
+                       self.lin_update.bias)
 
 
 class GossipCore(nn.Module):

@@ -268,6 +268,21 @@ int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_
                          int64_t workspace_bytes, int32_t precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Stand-alone message-passing primitives behind the callable leaf modules (csrc/conv.cu).  The hot path runs whole
+ * layer stacks fused; these serve code written against the reference's module API:
+ *   SAGEConv.forward   gnn_model.py:372-404  = desco_spmm_sum (propagate, aggr = "add") + desco_train_dense (lin)
+ *   GossipConv.forward gnn_model.py:303-359  = desco_gossip_gate, desco_train_dense (lin_com per node), desco_spmm_sum with
+ *                                              the per-edge gate weights, desco_train_dense (lin_update)
+ * desco_spmm_sum: out[i, 0:width] = sum over CSR row i (rowptr[n_dst+1], col) of edge_w[e] * x[col[e], 0:width]
+ * (edge_w NULL = 1).  desco_gossip_gate: gate[q] = LeakyReLU(sigmoid(w2 . sigmoid(W1 qemb[q] + b1) + b2)),
+ * W1 [hidden][emb_channels] row-major (nn.Linear layout), GossipConv.lin_gate / _gate_value (gnn_model.py:294-301,353).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int desco_spmm_sum(const int32_t* rowptr, const int32_t* col, const float* edge_w, int32_t n_dst, const float* x,
+                   int32_t ldx, int32_t width, float* out, int32_t ldo, void* stream);
+int desco_gossip_gate(const float* query_emb, int32_t num_queries, int32_t emb_channels, const float* w1, const float* b1,
+                      int32_t hidden, const float* w2, const float* b2, float* gate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Training step of the neighborhood-counting model (BASELINE config 3)
  * Replaces: NeighborhoodCountingModel.train_forward (lightning_model.py:228-254), criterion (:285-289),
  *           configure_optimizers / torch.optim.Adam (:160-173) and the autograd graph through gnn_model.py:58-109,
