@@ -407,6 +407,7 @@ def run_config5(ctx, args, nm, steps, warmup):
     pc_ms, pc_ms_min = ctx.reduce(my_ms, "max"), ctx.reduce(my_ms, "min")
     part_kernel_ms = ctx.reduce(pm[0], "max")
     shmp_kernel_ms = ctx.reduce(pm[1] + pm[2], "max")
+    shmp_layer_kernel_ms = ctx.reduce(pm[1], "max")
     st = pipe.last_stats
     G, V, E = (ctx.reduce(st[k], "sum") for k in ("neighborhoods", "rows", "directed_edges"))
     max_rows = int(ctx.reduce(st["max_rows"], "max"))
@@ -493,7 +494,8 @@ def run_config5(ctx, args, nm, steps, warmup):
                     "sharded by centre range (ranges balanced by estimated work), no collective; int32-safe chunks",
             "centres": int(len(sample)), "chunk_centres": args.c5_chunk, "neighborhoods": int(G), "rows": int(V),
             "directed_edges": int(E), "max_rows": max_rows, "ms": pc_ms, "ms_fastest_rank": pc_ms_min,
-            "partition_kernels_ms": part_kernel_ms, "shmp_kernels_ms": shmp_kernel_ms, "gpu_launches_rank0": int(pc_launches),
+            "partition_kernels_ms": part_kernel_ms, "shmp_kernels_ms": shmp_kernel_ms,
+            "of_which_shmp_layer_kernels_ms": shmp_layer_kernel_ms, "gpu_launches_rank0": int(pc_launches),
             "centres_per_s": len(sample) / (pc_ms * 1e-3), "neighborhoods_per_s": G / (pc_ms * 1e-3),
             "count_checksum": count_checksum,
         },

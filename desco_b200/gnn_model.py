@@ -43,6 +43,15 @@ def _key(et) -> str:
     return "__".join(et)
 
 
+_WEIGHTS_EPOCH = [0]  # bumped by anything that rewrites parameter storage behind autograd's back (training.FusedAdam.step)
+
+
+def bump_weights_epoch() -> None:
+    """Invalidate every packed-weight / query-embedding cache in the process.  Call after mutating parameters through a
+    path that neither bumps ``Parameter._version`` nor goes through ``load_state_dict`` / ``.to()`` / ``train()``."""
+    _WEIGHTS_EPOCH[0] += 1
+
+
 def _params_version(module: nn.Module) -> Tuple:
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
 
@@ -61,6 +70,13 @@ class _PackedWeightsMixin:
 
     def _invalidate_caches(self):
         self._cache_epoch += 1
+
+    def invalidate_caches(self):
+        """Public form: drop the derived weights after weight surgery in ``eval()`` mode (``p.data.copy_``, ``p.normal_``,
+        ``vector_to_parameters``, a torch optimizer step taken under ``no_grad`` + ``eval``): in pure inference the cache is
+        NOT revalidated against the parameters on every call (see the class docstring)."""
+        self._invalidate_caches()
+        return self
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
@@ -82,12 +98,13 @@ class _PackedWeightsMixin:
 
     def _cached(self, name: str, module: nn.Module, build):
         exact = self.training or torch.is_grad_enabled()
+        epoch = (self._cache_epoch, _WEIGHTS_EPOCH[0])
         hit = self._caches.get(name)
-        if hit is not None and hit[0] == self._cache_epoch and not exact:
+        if hit is not None and hit[0] == epoch and not exact:
             return hit[2]
         key = _params_version(module)
-        if hit is None or hit[0] != self._cache_epoch or hit[1] != key:
-            hit = (self._cache_epoch, key, build())
+        if hit is None or hit[0] != epoch or hit[1] != key:
+            hit = (epoch, key, build())
             self._caches[name] = hit
         return hit[2]
 

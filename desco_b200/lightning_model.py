@@ -79,7 +79,21 @@ def _load_lightning_checkpoint(cls, checkpoint_path, map_location=None, strict=T
     """``pl.LightningModule.load_from_checkpoint`` for the reference's ``.ckpt`` files (``main.py:216-233,319-334``): a
     pickled dict with ``state_dict`` (keys as produced by ``to_hetero_old``, SURVEY App. B.3 - the modules here use the
     same names) and ``hyper_parameters`` (the constructor arguments saved by ``save_hyperparameters()``)."""
-    ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+    try:  # tensors + plain containers + the argparse.Namespace of `args` only: no arbitrary pickle execution
+        import argparse
+        from types import SimpleNamespace as _SN
+
+        with torch.serialization.safe_globals([argparse.Namespace, _SN]):
+            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=True)
+    except Exception as safe_err:
+        # real Lightning checkpoints also pickle pytorch_lightning's AttributeDict (and need Lightning importable):
+        # opt in explicitly, the file is then trusted like any pickle
+        if not override.pop("trust_checkpoint", False):
+            raise RuntimeError(
+                f"{checkpoint_path}: not loadable with weights_only=True ({safe_err}); pass trust_checkpoint=True to unpickle "
+                "it fully (executes arbitrary code from the file; Lightning-written checkpoints also need pytorch_lightning)")
+        ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+    override.pop("trust_checkpoint", None)
     hp = dict(ckpt.get("hyper_parameters", {}))
     hp.update(override)
     model = cls(hp.pop("input_dim", 1), hp.pop("hidden_dim", 64), hp.pop("args", None), **hp)
@@ -102,6 +116,9 @@ class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
         self.emb_model = BaseGNN(input_dim, hidden_dim, hidden_dim, args, TARGET_META, emb_channels=hidden_dim, **kwargs)
         self.emb_model_query = BaseGNN(input_dim, hidden_dim, hidden_dim, args, QUERY_META, emb_channels=hidden_dim, **kwargs)
         self.count_model = nn.Sequential(nn.Linear(2 * hidden_dim, 4 * hidden_dim), nn.LeakyReLU(), nn.Linear(4 * hidden_dim, 1))
+        # the reference collates DataLoader batches of args.batch_size neighborhoods (config.py:255): the default unit over
+        # which SAGEConv's remove_self_loops quirk is evaluated (set_pyg_batch_size changes it)
+        self.emb_model.pyg_batch_size = int(getattr(args, "batch_size", 0) or 0)
         self._init_cache()
 
     # ---- the reference converts with pyg.nn.to_hetero at run time; these modules are built hetero ----

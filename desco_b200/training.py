@@ -443,4 +443,9 @@ class FusedAdam(torch.optim.Optimizer):
                                             self.flat_p.numel(), float(grp["lr"]), float(grp["betas"][0]),
                                             float(grp["betas"][1]), float(grp["eps"]), float(grp["weight_decay"]),
                                             self.step_count, _stream()), "desco_train_adam")
+        # the update went through a raw pointer: no Parameter._version moved, so the packed-weight / query-embedding
+        # caches of the models (gnn_model._PackedWeightsMixin) must be told
+        from .gnn_model import bump_weights_epoch
+
+        bump_weights_epoch()
         return loss

@@ -38,6 +38,7 @@ def as_device_csr(dataset, device=None) -> DeviceCSR:
         gl = []
         for g in graphs:
             ei = g.edge_index.detach().cpu().numpy().T.reshape(-1, 2)
+            ei = ei[ei[:, 0] <= ei[:, 1]]  # to_networkx(to_undirected=True) keeps u <= v only (workload.py:224; data._to_nx_graph)
             gl.append((int(g.num_nodes), ei))
         return DeviceCSR.from_host(csr_from_graph_list(gl), device)
     return DeviceCSR.from_host(csr_from_networkx(graphs), device)

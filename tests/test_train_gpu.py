@@ -153,3 +153,42 @@ def test_training_then_inference_uses_new_weights(cuda_device):
     with torch.no_grad():
         after = pm.graph_to_count(batch)
     assert (after - before).abs().max().item() > 0
+
+
+def test_monitoring_in_train_mode_sees_every_optimizer_step(cuda_device):
+    """FusedAdam updates the flat parameter buffer through a raw pointer (no Parameter._version moves): calling
+    graph_to_count / get_query_emb between steps WITHOUT an eval()/train() toggle - periodic monitoring inside a training
+    loop - must still see the new weights, in both grad modes."""
+    om, pm, b_np, batch, y = _setup(gen_mutag_shaped(seed=7, num_graphs=8), seed=4)
+    pm.train()
+    opt = pm.configure_optimizers()["optimizer"]
+    for g in opt.param_groups:
+        g["lr"] = 1e-2
+    seen, seen_q = [], []
+    for step in range(3):
+        with torch.no_grad():
+            seen.append(pm.graph_to_count(batch).clone())
+            seen_q.append(pm.get_query_emb().clone())
+        opt.zero_grad()
+        pm.training_step(batch, step).backward()
+        opt.step()
+    with torch.no_grad():
+        seen.append(pm.graph_to_count(batch).clone())
+    assert all((a - b).abs().max().item() > 0 for a, b in zip(seen[:-1], seen[1:]))
+    assert all((a - b).abs().max().item() > 0 for a, b in zip(seen_q[:-1], seen_q[1:]))
+    # eval + no_grad after an optimizer step taken while already in eval mode (the frozen-cache regime)
+    pm.eval()
+    with torch.no_grad():
+        a = pm.graph_to_count(batch).clone()
+    pm.train_forward(batch).backward()
+    opt.step()
+    with torch.no_grad():
+        b = pm.graph_to_count(batch)
+    assert (a - b).abs().max().item() > 0
+    # weight surgery in eval mode needs the public invalidate_caches()
+    with torch.no_grad():
+        pm.count_model[2].bias.add_(1.0)
+        pm.invalidate_caches()
+        c = pm.graph_to_pred(batch)
+        b_pred = torch.log2(b + 1)
+    assert ((c - b_pred) - 1.0).abs().max().item() < 1e-3
