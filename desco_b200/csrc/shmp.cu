@@ -27,15 +27,11 @@ constexpr int THREADS = 256;
 // ------------------------------------------------------------------------------------------------------------------
 // plan: per-row metadata derived from the packed batch
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void shmp_plan_kernel(const int32_t* __restrict__ nbh_ptr, const int32_t* __restrict__ edge_ptr,
-                                 const int32_t* __restrict__ edge_col, const uint8_t* __restrict__ edge_tri, int G,
-                                 int hetero, int pyg_batch_size, int32_t* __restrict__ row_nbh,
-                                 int32_t* __restrict__ crow, uint8_t* __restrict__ canon_code,
+// one thread per neighborhood: the row whose edge to the canonical node SAGEConv's remove_self_loops drops
+__global__ void shmp_plan_kernel(const int32_t* __restrict__ nbh_ptr, int G, int hetero, int pyg_batch_size,
                                  int32_t* __restrict__ quirk_row) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
-  const int lane = lane_id();
-  const int lo = nbh_ptr[g], hi = nbh_ptr[g + 1];
   int quirk = -1;
   if (hetero) {
     // SAGEConv.forward runs remove_self_loops on the bipartite count<->canonical relations too (gnn_model.py:389-390):
@@ -43,24 +39,39 @@ __global__ void shmp_plan_kernel(const int32_t* __restrict__ nbh_ptr, const int3
     // edge canonical(g) -- first row of g, iff every earlier neighborhood of the PyG batch has exactly two rows.
     const int bs = pyg_batch_size > 0 ? pyg_batch_size : G;
     const int g0 = (g / bs) * bs;
+    const int lo = nbh_ptr[g];
     if (pyg_batch_size >= 0 && lo - nbh_ptr[g0] == 2 * (g - g0)) quirk = lo;  // pyg_batch_size < 0: quirk off
-    if (lane == 0) quirk_row[g] = quirk;
   }
-  const int canon = hi - 1;
-  for (int r = lo + lane; r < hi; r += 32) {
-    row_nbh[r] = g;
-    if (!hetero) {
-      crow[r] = r;
-      canon_code[r] = 0;
-    } else if (r < canon) {
-      crow[r - g] = r;
-      uint8_t code = 0;
-      const int eb = edge_ptr[r], ee = edge_ptr[r + 1];
-      if (ee > eb && edge_col[ee - 1] == canon && r != quirk) code = edge_tri[ee - 1] ? 1 : 2;  // canon = max row of g
-      canon_code[r] = code;
-    } else {
-      canon_code[r] = 0;
-    }
+  quirk_row[g] = quirk;
+}
+
+// one thread per packed row (a neighborhood may hold 10^6 rows: config 5): its neighborhood by binary search, its compact
+// count-row slot and how it touches its canonical node
+__global__ void shmp_plan_rows_kernel(const int32_t* __restrict__ nbh_ptr, const int32_t* __restrict__ edge_ptr,
+                                      const int32_t* __restrict__ edge_col, const uint8_t* __restrict__ edge_tri, int G, int V,
+                                      int hetero, const int32_t* __restrict__ quirk_row, int32_t* __restrict__ row_nbh,
+                                      int32_t* __restrict__ crow, uint8_t* __restrict__ canon_code) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= V) return;
+  int lo = 0, hi = G;  // largest g with nbh_ptr[g] <= r
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (nbh_ptr[mid] <= r) lo = mid; else hi = mid;
+  }
+  const int g = lo;
+  row_nbh[r] = g;
+  const int canon = nbh_ptr[g + 1] - 1;
+  if (!hetero) {
+    crow[r] = r;
+    canon_code[r] = 0;
+  } else if (r < canon) {
+    crow[r - g] = r;
+    uint8_t code = 0;
+    const int eb = edge_ptr[r], ee = edge_ptr[r + 1];
+    if (ee > eb && edge_col[ee - 1] == canon && r != quirk_row[g]) code = edge_tri[ee - 1] ? 1 : 2;  // canon = max row of g
+    canon_code[r] = code;
+  } else {
+    canon_code[r] = 0;
   }
 }
 
@@ -443,9 +454,10 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
     if (rc) return rc;
   } else {
   {
-    DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
-    shmp_plan_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, edge_ptr, edge_col, edge_tri, G, hetero,
-                                                         pyg_batch_size, ws.row_nbh, ws.crow, ws.canon_code, ws.quirk_row);
+    DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s, 2);
+    shmp_plan_kernel<<<(G + 255) / 256, 256, 0, s>>>(nbh_ptr, G, hetero, pyg_batch_size, ws.quirk_row);
+    shmp_plan_rows_kernel<<<(V + 255) / 256, 256, 0, s>>>(nbh_ptr, edge_ptr, edge_col, edge_tri, G, V, hetero, ws.quirk_row,
+                                                         ws.row_nbh, ws.crow, ws.canon_code);
     DESCO_LAUNCH_CHECK();
   }
   {

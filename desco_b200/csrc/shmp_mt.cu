@@ -26,18 +26,18 @@ namespace {
 constexpr int F = 64;
 constexpr int TR = 128;                      // rows per tile = UMMA M
 constexpr int KB = 3;                        // 64-wide K blocks: tri | tride | self
-constexpr int THREADS = 1024;
-constexpr int NW = THREADS / 32;
-constexpr int EPI_WARPS = 16;                // warps 0..15 run the epilogue, the rest run ahead into the next gather
-constexpr int HUB_DEG = 2048;                // rows with more edges are gathered by the whole CTA
+constexpr int THREADS = 512;
+constexpr int NW = THREADS / 32;             // 16 warps x 128 registers (16 row loads in flight each); rows of a tile are dealt by a ticket
+constexpr int EPI_WARPS = 16;                // the warps that run the epilogue (4 lane quarters x 4 column groups)
+constexpr int HUB_DEG = 1024;                // rows with more edges are gathered by the whole CTA
 constexpr int IMG = TR * 128;                // one bf16 image of a [128 x 64] block
 constexpr int B_IMG = F * 128;               // one bf16 image of a [64 n x 64 k] weight block
 constexpr int SM_B = 0;                                  // [KB][hi | lo] weight images, 48 KB
 constexpr int SM_A = SM_B + KB * 2 * B_IMG;              // [KB][hi | lo] operand images, 96 KB
 constexpr int SM_ROW = SM_A + KB * 2 * IMG;              // 2 x { int s_row[TR], s_g[TR], s_code[TR] }
-constexpr int SM_HUB = SM_ROW + 2 * 3 * TR * 4;          // float4 s_hub[NW][32]
-constexpr int SM_BIAS = SM_HUB + NW * 32 * 16;           // float bias[64]
-constexpr int SM_BARS = SM_BIAS + F * 4;                 // 2 mbarriers, tmem slot, hub list
+constexpr int SM_HUB = SM_ROW + 2 * 3 * TR * 4;          // float4 s_hub[NW][16][2]
+constexpr int SM_BIAS = SM_HUB + NW * 16 * 32;           // float bias[64]
+constexpr int SM_BARS = SM_BIAS + F * 4;                 // 2 mbarriers, tmem slot, hub count, 2 row tickets, hub list
 constexpr int SM_TOTAL = SM_BARS + 64 + TR;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 static_assert(SM_A % 1024 == 0 && B_IMG % 1024 == 0 && IMG % 1024 == 0, "UMMA tiles must be 1024-B aligned");
@@ -54,44 +54,63 @@ struct MtArgs {
   int32_t* status;
 };
 
-__device__ __forceinline__ void add_sel(float2& at, float2& ad, const float2 v, int s) {
-  if (s < 0) { at.x += v.x; at.y += v.y; } else { ad.x += v.x; ad.y += v.y; }
-}
+__device__ __forceinline__ void add4(float4& a, const float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
 
-// sum over edges [eb, ee) (stride `step` chunks of 32 starting at eb + 32 * first), split by SHMP type (bit 31 of the
-// packed source word).  Four independent 256-byte row loads are in flight per warp.
-__device__ __forceinline__ void gather_edges(const float* __restrict__ h, const int32_t* __restrict__ edge_col,
-                                             const uint8_t* __restrict__ edge_tri, int eb, int ee, int first, int step,
-                                             int lane, float2& at, float2& ad) {
-  for (int base = eb + 32 * first; base < ee; base += 32 * step) {
-    const int e = base + lane;
-    int my = 0;
-    if (e < ee) my = edge_col[e] | (edge_tri[e] ? (int)0x80000000 : 0);
-    const int n = min(32, ee - base);
-    int j = 0;
-    for (; j + 4 <= n; j += 4) {
-      const int s0 = __shfl_sync(FULL_MASK, my, j), s1 = __shfl_sync(FULL_MASK, my, j + 1);
-      const int s2 = __shfl_sync(FULL_MASK, my, j + 2), s3 = __shfl_sync(FULL_MASK, my, j + 3);
-      const float2 v0 = __ldg(reinterpret_cast<const float2*>(h + (size_t)(s0 & 0x7fffffff) * F) + lane);
-      const float2 v1 = __ldg(reinterpret_cast<const float2*>(h + (size_t)(s1 & 0x7fffffff) * F) + lane);
-      const float2 v2 = __ldg(reinterpret_cast<const float2*>(h + (size_t)(s2 & 0x7fffffff) * F) + lane);
-      const float2 v3 = __ldg(reinterpret_cast<const float2*>(h + (size_t)(s3 & 0x7fffffff) * F) + lane);
-      add_sel(at, ad, v0, s0); add_sel(at, ad, v1, s1); add_sel(at, ad, v2, s2); add_sel(at, ad, v3, s3);
-    }
-    for (; j < n; ++j) {
-      const int s = __shfl_sync(FULL_MASK, my, j);
-      add_sel(at, ad, __ldg(reinterpret_cast<const float2*>(h + (size_t)(s & 0x7fffffff) * F) + lane), s);
-    }
+// D rows (two per warp instruction: a half-warp per 256-byte row, 16 bytes per lane) of one 32-edge chunk in flight
+template <int D>
+__device__ __forceinline__ void gather_chunk(const float* __restrict__ h, int cur, int n, int half, int l16, float4& at,
+                                             float4& ad) {
+  float4 v[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const int j = 2 * i + half;
+    const int s = __shfl_sync(FULL_MASK, cur, j);
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < n) v[i] = __ldg(reinterpret_cast<const float4*>(h + (size_t)(s & 0x7fffffff) * F) + l16);
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const int s = __shfl_sync(FULL_MASK, cur, 2 * i + half);
+    if (s < 0) add4(at, v[i]); else add4(ad, v[i]);  // bit 31 = triangle edge (a padded slot is 0 and adds 0 to tride)
   }
 }
 
-__device__ __forceinline__ void store_pair(uint8_t* img, int r, int lane, float2 v) {  // bf16 hi / lo, swizzled
-  const uint32_t off = tc05::sw128_offset(r, 2 * lane);
-  const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
-  const float2 f = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(v.x - f.x, v.y - f.y);
-  *reinterpret_cast<__nv_bfloat162*>(img + off) = h;
-  *reinterpret_cast<__nv_bfloat162*>(img + IMG + off) = l;
+// sum over edges [eb, ee) in 32-edge chunks `first`, `first + step`, ..., split by SHMP type (bit 31 of the packed
+// source word).  Lane = (edge parity, 4 features): on return every lane of BOTH halves holds the sums of its 4 features.
+// The next chunk's sources load while the current chunk's (up to 32) rows are in flight.
+__device__ __forceinline__ void gather_edges(const float* __restrict__ h, const int32_t* __restrict__ edge_col,
+                                             const uint8_t* __restrict__ edge_tri, int eb, int ee, int first, int step,
+                                             int lane, float4& at, float4& ad) {
+  const int half = lane >> 4, l16 = lane & 15;
+  int base = eb + 32 * first;
+  int my = 0;
+  if (base + lane < ee) my = edge_col[base + lane] | (edge_tri[base + lane] ? (int)0x80000000 : 0);
+  while (base < ee) {
+    const int n = min(32, ee - base);
+    const int cur = my;
+    base += 32 * step;
+    my = 0;
+    if (base + lane < ee) my = edge_col[base + lane] | (edge_tri[base + lane] ? (int)0x80000000 : 0);
+    if (n <= 8) gather_chunk<4>(h, cur, n, half, l16, at, ad);
+    else if (n <= 16) gather_chunk<8>(h, cur, n, half, l16, at, ad);
+    else gather_chunk<16>(h, cur, n, half, l16, at, ad);
+  }
+#define DESCO_XH(a) a += __shfl_xor_sync(FULL_MASK, a, 16)
+  DESCO_XH(at.x); DESCO_XH(at.y); DESCO_XH(at.z); DESCO_XH(at.w);
+  DESCO_XH(ad.x); DESCO_XH(ad.y); DESCO_XH(ad.z); DESCO_XH(ad.w);
+#undef DESCO_XH
+}
+
+// 4 consecutive features of row r as bf16 hi / lo, swizzled (8-byte stores; 16 lanes cover the 128-byte row)
+__device__ __forceinline__ void store_quad(uint8_t* img, int r, int l16, float4 v) {
+  const uint32_t off = tc05::sw128_offset(r, 4 * l16);
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+  *reinterpret_cast<uint2*>(img + off) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  *reinterpret_cast<uint2*>(img + IMG + off) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
 }
 
 __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs p) {
@@ -107,9 +126,11 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);  // [0] weights, [1] MMA done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   int* s_nhub = reinterpret_cast<int*>(tmem_slot + 1);
+  int* s_ticket = s_nhub + 1;  // [2], by tile parity
   uint8_t* s_hubs = reinterpret_cast<uint8_t*>(bars) + 64;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = lane >> 4, l16 = lane & 15;
   if ((int)blockIdx.x >= p.num_tiles) return;
   if (tid == 0) {
     tc05::mbar_init(&bars[0], 1);
@@ -145,6 +166,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
       s_g[b * 3 * TR + tid] = g;
       s_code[b * 3 * TR + tid] = code;
     }
+    if (tid == TR) s_ticket[b] = 0;
   };
   setup(blockIdx.x, 0);
   if (tid == 0) *s_nhub = 0;
@@ -156,41 +178,42 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
     const int* t_g = s_g + buf * 3 * TR;
     const int* t_code = s_code + buf * 3 * TR;
 
-    // ---- gather: [sum tri | sum tride | self] of every row -> bf16 hi/lo operand images ----
+    // ---- gather: [sum tri | sum tride | self] of every row -> bf16 hi/lo operand images; rows are dealt by a ticket, so a
+    //      warp that drew a long row (or is still in the previous tile's epilogue) simply takes fewer of them ----
 #pragma unroll 1
-    for (int r = warp; r < TR; r += NW) {
+    for (;;) {
+      int r = 0;
+      if (lane == 0) r = atomicAdd(&s_ticket[buf], 1);
+      r = __shfl_sync(FULL_MASK, r, 0);
+      if (r >= TR) break;
       const int row = t_row[r];
-      float2 at = make_float2(0.f, 0.f), ad = at, self = at;
+      float4 at = make_float4(0.f, 0.f, 0.f, 0.f), ad = at, self = at;
       bool hub = false;
       if (row >= 0) {
-        self = __ldg(reinterpret_cast<const float2*>(p.h_in + (size_t)row * F) + lane);
+        if (half == 0) self = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)row * F) + l16);
         const int eb = p.edge_ptr[row], ee = p.edge_ptr[row + 1];
         hub = ee - eb > HUB_DEG;
         if (!hub) gather_edges(p.h_in, p.edge_col, p.edge_tri, eb, ee, 0, 1, lane, at, ad);
         else if (lane == 0) s_hubs[atomicAdd(s_nhub, 1)] = (uint8_t)r;
       }
-      if (!hub) {
-        store_pair(sA, r, lane, at);
-        store_pair(sA + 2 * IMG, r, lane, ad);
-      }
-      store_pair(sA + 4 * IMG, r, lane, self);
+      if (!hub) store_quad(sA + (half ? 2 * IMG : 0), r, l16, half ? ad : at);  // the two halves write one block each
+      if (half == 0) store_quad(sA + 4 * IMG, r, l16, self);
     }
     __syncthreads();  // every warp is past the previous tile's epilogue here: the other metadata buffer is free
     setup(tile + gridDim.x, buf ^ 1);
     for (int hh = 0, nh = *s_nhub; hh < nh; ++hh) {  // hub rows: 32-edge chunks dealt over all warps, summed in warp order
       const int r = s_hubs[hh], row = t_row[r];
-      float2 at = make_float2(0.f, 0.f), ad = at;
+      float4 at = make_float4(0.f, 0.f, 0.f, 0.f), ad = at;
       gather_edges(p.h_in, p.edge_col, p.edge_tri, p.edge_ptr[row], p.edge_ptr[row + 1], warp, NW, lane, at, ad);
-      s_hub[warp * 32 + lane] = make_float4(at.x, at.y, ad.x, ad.y);
+      if (half == 0) {
+        s_hub[(warp * 16 + l16) * 2] = at;
+        s_hub[(warp * 16 + l16) * 2 + 1] = ad;
+      }
       __syncthreads();
       if (warp == 0) {
-        float4 t = s_hub[lane];
-        for (int w = 1; w < NW; ++w) {
-          const float4 o = s_hub[w * 32 + lane];
-          t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
-        }
-        store_pair(sA, r, lane, make_float2(t.x, t.y));
-        store_pair(sA + 2 * IMG, r, lane, make_float2(t.z, t.w));
+        float4 t = s_hub[l16 * 2 + half];  // half 0 sums the triangle partials, half 1 the tride partials
+        for (int w = 1; w < NW; ++w) add4(t, s_hub[(w * 16 + l16) * 2 + half]);
+        store_quad(sA + (half ? 2 * IMG : 0), r, l16, t);
       }
       __syncthreads();
     }
@@ -259,6 +282,10 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
 // ------------------------------------------------------------------------------------------------------------------
 // canonical rows: emb_a[g][(l+1)F..] = relu( [sum_tri h_c | sum_tride h_c | h_a] . Wa + bias_a ), one CTA per neighborhood
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void add_sel(float2& at, float2& ad, const float2 v, int s) {
+  if (s < 0) { at.x += v.x; at.y += v.y; } else { ad.x += v.x; ad.y += v.y; }
+}
+
 constexpr int CT = 256;
 __global__ void __launch_bounds__(CT) shmp_mt_canon_kernel(const int32_t* __restrict__ nbh_ptr, const int32_t* __restrict__ edge_ptr,
                                                            const int32_t* __restrict__ edge_col, const uint8_t* __restrict__ edge_tri,
