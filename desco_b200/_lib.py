@@ -115,6 +115,7 @@ SIGNATURES = {
     "desco_gossip_layer0_grouped": (_I, [_VP, _VP, _I, _I, _VP, _I, _VP, _VP, _I, _L, _VP]),
     "desco_gossip_layer1_group": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _I, _I, _VP, _L, _VP]),
     "desco_gossip_layer1_workspace_bytes": (_L, [_I, _I, _I]),
+    "desco_groundtruth_count": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP]),
     "desco_spmm_sum": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _VP, _I, _VP]),
     "desco_gossip_gate": (_I, [_VP, _I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
     "desco_shmp_fused_phase_cycles": (_I, [_VP, _I]),

@@ -189,6 +189,45 @@ class Workload:
             self.neighborhood_dataset.apply_truth_from_dataset(self.canonical_count_truth)
             self.gossip_dataset.apply_truth_from_dataset(self.canonical_count_truth)
 
+    # ---- ground truth (labels): workload.py:473-726 ----
+    max_file_name_len = 30  # workload.py:412
+
+    def _truth_file(self, query_ids, queries) -> str:
+        """File name scheme of the reference (``workload.py:484-507``) so existing label caches are found."""
+        if (query_ids is None) == (queries is None):
+            raise ValueError("query_ids or queries must be given (and not both)")
+        if query_ids is not None:
+            name = "query_num_{:d}_".format(len(query_ids)) + "atlas_ids_" + "_".join(map(str, query_ids[: self.max_file_name_len])) + ".pt"
+        else:
+            name = "query_num_{:d}_".format(len(queries)) + "query_len_sum_" + str(sum(len(g) for g in queries)) + ".pt"
+        return os.path.join(self.root, "CanonicalCountTruth", name)
+
+    def exist_groundtruth(self, query_ids, queries=None) -> bool:
+        """``workload.py:512-549``."""
+        return self.root is not None and os.path.exists(self._truth_file(query_ids, queries))
+
+    def load_groundtruth(self, query_ids, queries=None) -> torch.Tensor:
+        """``workload.py:473-510``: the cached ``count_motif`` tensor (plain ``torch.save`` of a tensor)."""
+        if not self.exist_groundtruth(query_ids, queries):
+            raise NotImplementedError
+        self.canonical_count_truth = torch.load(self._truth_file(query_ids, queries), weights_only=True)
+        return self.canonical_count_truth
+
+    def compute_groundtruth(self, query_ids=None, queries=None, num_workers=-1, save_to_file=True) -> torch.Tensor:
+        """``workload.py:551-726``: canonical counts of every query at every node, [#node, #query] - on the GPU
+        (csrc/groundtruth.cu) instead of one networkx VF2 process per (target, query); ``num_workers`` is ignored."""
+        from .groundtruth import canonical_count_truth
+
+        truth = canonical_count_truth(self.graph, query_ids=query_ids, queries=queries).cpu()
+        self.query_ids = list(query_ids) if query_ids is not None else [-i for i in range(len(queries))]
+        self.queries = queries
+        self.canonical_count_truth = truth
+        if save_to_file and self.root is not None:
+            path = self._truth_file(query_ids, queries)
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            torch.save(truth, path)
+        return truth
+
     def apply_neighborhood_count(self, count):
         self.gossip_dataset.apply_neighborhood_count(count, self.neighborhood_dataset.nx_neighs_indicator)
 

@@ -268,6 +268,21 @@ int desco_gossip_forward(const int32_t* rowptr, const int32_t* col, int32_t num_
                          int64_t workspace_bytes, int32_t precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Ground-truth canonical counts (labels)
+ * Replaces: MatchSubgraphWorker (workload.py:327-348, networkx VF2 per (target, query), every mapping credited to
+ *           max(vmap.keys())), Workload.compute_groundtruth (workload.py:551-726) and the division by SymmetricFactor
+ *           (data.py:61-88): out_counts[node, q] = number of node sets whose induced subgraph is isomorphic to query q and
+ *           whose largest node is `node` (int64, caller-zeroed).  Connected queries of 3..5 nodes.
+ * lut3 / lut4 / lut5: uint8[8] / [64] / [1024], adjacency pattern of a node tuple (bit of pair (i, j), i < j, at position
+ * j(j-1)/2 + i) -> query column, 255 = none (desco_b200.groundtruth.pattern_tables).  Graphs up to 1024 nodes (the
+ * adjacency bit-matrix of a graph lives in shared memory); status receives DESCO_ERANGE otherwise.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int desco_groundtruth_count(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
+                            int32_t max_graph_nodes, const uint8_t* lut3, const uint8_t* lut4, const uint8_t* lut5,
+                            int32_t num_queries, int32_t max_query_nodes, int64_t* out_counts, int32_t* status,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Stand-alone message-passing primitives behind the callable leaf modules (csrc/conv.cu).  The hot path runs whole
  * layer stacks fused; these serve code written against the reference's module API:
  *   SAGEConv.forward   gnn_model.py:372-404  = desco_spmm_sum (propagate, aggr = "add") + desco_train_dense (lin)

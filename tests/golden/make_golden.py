@@ -272,6 +272,23 @@ def main():
     print("pipeline golden", len(b["centre"]), "neighborhoods; first count node in networkx order is the lowest id in",
           int(first_low.sum()), "of", len(first_low), "; count range", counts.min().item(), counts.max().item())
 
+    # ---------------- ground-truth canonical counts: the reference's own VF2 worker + symmetry factor ----------------
+    from oracle import groundtruth as GT
+
+    gt_funcs = GT.reference_functions()
+    queries = [nx.graph_atlas(i) for i in M.STANDARD_QUERY_IDS]
+    dense = [nx.gnm_random_graph(12, 34, seed=3), nx.complete_graph(6), nx.star_graph(7), nx.cycle_graph(9)]
+    gsets = {"kat": csr_from_networkx(kat_graphs() + dense), "mutag": gen_mutag_shaped(seed=8, num_graphs=10),
+             "enzymes": gen_enzymes_shaped(seed=8, num_graphs=3), "imdb": gen_imdb_shaped(seed=8, num_graphs=2)}
+    out = {}
+    for name, csr in gsets.items():
+        truth = GT.canonical_count_truth(csr, queries, gt_funcs)
+        assert np.array_equal(truth, np.round(truth))
+        out.update({f"{name}_rowptr": csr.rowptr, f"{name}_col": csr.col, f"{name}_graph_ptr": csr.graph_ptr,
+                    f"{name}_truth": truth.astype(np.int64)})
+        print("ground truth golden", name, csr.num_nodes, "nodes, total occurrences", int(truth.sum()))
+    np.savez_compressed(os.path.join(HERE, "groundtruth_ref.npz"), query_ids=np.asarray(M.STANDARD_QUERY_IDS), **out)
+
 
 if __name__ == "__main__":
     main()

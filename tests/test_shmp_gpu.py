@@ -31,12 +31,17 @@ def _models(seed=0, bias_shift=None):
     return om, pm
 
 
-def _check(om, pm, b_np, pyg_bs=None, tol=TOL, precision="bf16x3", multi_tile=False):
+def _check(om, pm, b_np, pyg_bs=None, tol=TOL, precision="bf16x3", multi_tile=False, oracle64=False):
     from desco_b200.data import NeighborhoodBatch
     from oracle import model as M
 
     with torch.no_grad():
-        ref_pred = om.pre_exponent(b_np, M.query_batch(), pyg_batch_size=pyg_bs)
+        if oracle64:  # neighborhoods of 10^3 rows: the fp32 oracle's own index_add sums drift by ~1e-4; judge against fp64
+            import copy
+
+            ref_pred = copy.deepcopy(om).double().pre_exponent(b_np, M.query_batch(), pyg_batch_size=pyg_bs).float()
+        else:
+            ref_pred = om.pre_exponent(b_np, M.query_batch(), pyg_batch_size=pyg_bs)
     ref_count = 2 ** ref_pred - 1
     batch = NeighborhoodBatch.from_numpy(b_np)
     pm.set_pyg_batch_size(pyg_bs or 0)
@@ -176,7 +181,7 @@ def test_multi_tile_path_hub_rows_and_query_graphs(cuda_device):
     centres = np.array([n - 1, n - 2, 1500])
     b = P.partition_dataset(csr, 2, centres=centres)
     assert np.diff(b["edge_ptr"]).max() > 2048  # a hub row
-    _check(om, pm, b, precision="bf16x3")
+    _check(om, pm, b, precision="bf16x3", oracle64=True)
     pm.emb_model_query.force_multi_tile = True
     pm.emb_model_query.precision = "bf16x3"
     pm._invalidate_caches()

@@ -153,7 +153,7 @@ def test_sage_and_gossip_conv_modules_are_callable_like_the_reference(cuda_devic
         eu = eu[:, eu[0] != eu[1]]
         w = eu[0] < eu[1]
         with torch.no_grad():
-            got = gc(xg, eu, w, qe)
+            got = gc(xg, eu, edge_weight=w, query_emb=qe)  # keyword call, like gnn_model.py:258-260
             gate = gc.lin_gate(qe)
             msg = gc.lin_com(xg[eu[0]])
             msg = torch.where(w.view(-1, 1), msg * gate, msg * (1 - gate))
