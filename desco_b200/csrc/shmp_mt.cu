@@ -27,17 +27,17 @@ constexpr int F = 64;
 constexpr int TR = 128;                      // rows per tile = UMMA M
 constexpr int KB = 3;                        // 64-wide K blocks: tri | tride | self
 constexpr int THREADS = 512;
-constexpr int NW = THREADS / 32;             // 16 warps x 128 registers: a half-warp per row, 16 row loads in flight each
+constexpr int NW = THREADS / 32;             // 16 warps x 128 registers (16 row loads in flight each); rows of a tile are dealt by a ticket
 constexpr int EPI_WARPS = 16;                // the warps that run the epilogue (4 lane quarters x 4 column groups)
-constexpr int HUB_DEG = 512;                 // rows with more edges are gathered by the whole CTA
+constexpr int HUB_DEG = 1024;                // rows with more edges are gathered by the whole CTA
 constexpr int IMG = TR * 128;                // one bf16 image of a [128 x 64] block
 constexpr int B_IMG = F * 128;               // one bf16 image of a [64 n x 64 k] weight block
 constexpr int SM_B = 0;                                  // [KB][hi | lo] weight images, 48 KB
 constexpr int SM_A = SM_B + KB * 2 * B_IMG;              // [KB][hi | lo] operand images, 96 KB
 constexpr int SM_ROW = SM_A + KB * 2 * IMG;              // 2 x { int s_row, s_g, s_code, s_eb, s_ee [TR] }
-constexpr int SM_HUB = SM_ROW + 2 * 5 * TR * 4;          // float4 s_hub[2 NW half-warps][16][2]
-constexpr int SM_BIAS = SM_HUB + 2 * NW * 16 * 32;       // float bias[64]
-constexpr int SM_BARS = SM_BIAS + F * 4;                 // 2 mbarriers, tmem slot, hub count, hub list
+constexpr int SM_HUB = SM_ROW + 2 * 5 * TR * 4;          // float4 s_hub[NW][16][2]
+constexpr int SM_BIAS = SM_HUB + NW * 16 * 32;           // float bias[64]
+constexpr int SM_BARS = SM_BIAS + F * 4;                 // 2 mbarriers, tmem slot, hub count, 2 row tickets, hub list
 constexpr int SM_TOTAL = SM_BARS + 64 + TR;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 static_assert(SM_A % 1024 == 0 && B_IMG % 1024 == 0 && IMG % 1024 == 0, "UMMA tiles must be 1024-B aligned");
@@ -56,48 +56,49 @@ struct MtArgs {
 
 __device__ __forceinline__ void add4(float4& a, const float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
 
-__device__ __forceinline__ int edge_word(const int32_t* __restrict__ edge_col, const uint8_t* __restrict__ edge_tri, int e) {
-  return edge_col[e] | (edge_tri[e] ? (int)0x80000000 : 0);  // source row | triangle flag in bit 31
-}
-
-// A HALF-WARP owns a row: lane l16 holds features 4 l16 .. 4 l16 + 3, a 256-byte source row is one 16-byte load per lane, and
-// the two halves of a warp walk two different rows at once.  Edges [eb, ee) in chunks of 16 (`first`, `first + step`, ...):
-// the lanes of the half fetch the chunk's source words (the NEXT chunk's while this chunk's rows are in flight), then up
-// to 16 row loads are issued back to back.  `cur` = the first chunk's words, prefetched by the caller.  Every shuffle
-// is executed by the whole warp (width 16); a half that has run out of chunks just adds nothing.
+// D rows (two per warp instruction: a half-warp per 256-byte row, 16 bytes per lane) of one 32-edge chunk in flight
 template <int D>
-__device__ __forceinline__ void gather_chunk(const float* __restrict__ h, int cur, int n, int l16, float4& at, float4& ad) {
+__device__ __forceinline__ void gather_chunk(const float* __restrict__ h, int cur, int n, int half, int l16, float4& at,
+                                             float4& ad) {
   float4 v[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    const int s = __shfl_sync(FULL_MASK, cur, i, 16);
+    const int j = 2 * i + half;
+    const int s = __shfl_sync(FULL_MASK, cur, j);
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < n) v[i] = __ldg(reinterpret_cast<const float4*>(h + (size_t)(s & 0x7fffffff) * F) + l16);
+    if (j < n) v[i] = __ldg(reinterpret_cast<const float4*>(h + (size_t)(s & 0x7fffffff) * F) + l16);
   }
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    const int s = __shfl_sync(FULL_MASK, cur, i, 16);
-    if (s < 0) add4(at, v[i]); else add4(ad, v[i]);  // (an empty slot holds 0 and adds zeros to the tride sum)
+    const int s = __shfl_sync(FULL_MASK, cur, 2 * i + half);
+    if (s < 0) add4(at, v[i]); else add4(ad, v[i]);  // bit 31 = triangle edge (a padded slot is 0 and adds 0 to tride)
   }
 }
 
+// sum over edges [eb, ee) in 32-edge chunks `first`, `first + step`, ..., split by SHMP type (bit 31 of the packed
+// source word).  Lane = (edge parity, 4 features): on return every lane of BOTH halves holds the sums of its 4 features.
+// The next chunk's sources load while the current chunk's (up to 32) rows are in flight.
 __device__ __forceinline__ void gather_edges(const float* __restrict__ h, const int32_t* __restrict__ edge_col,
                                              const uint8_t* __restrict__ edge_tri, int eb, int ee, int first, int step,
-                                             int l16, int cur, float4& at, float4& ad) {
-  int base = eb + 16 * first;
-  // warp-uniform trip count: the longer of the two halves' rows
-  int chunks = base < ee ? (ee - base + 16 * step - 1) / (16 * step) : 0;
-  chunks = max(chunks, __shfl_xor_sync(FULL_MASK, chunks, 16));
-  for (int c = 0; c < chunks; ++c) {
-    const int n = max(0, min(16, ee - base));
-    const int mine = cur;
-    base += 16 * step;
-    cur = (base + l16 < ee) ? edge_word(edge_col, edge_tri, base + l16) : 0;
-    int nmax = max(n, __shfl_xor_sync(FULL_MASK, n, 16));
-    if (nmax <= 4) gather_chunk<4>(h, mine, n, l16, at, ad);
-    else if (nmax <= 8) gather_chunk<8>(h, mine, n, l16, at, ad);
-    else gather_chunk<16>(h, mine, n, l16, at, ad);
+                                             int lane, float4& at, float4& ad) {
+  const int half = lane >> 4, l16 = lane & 15;
+  int base = eb + 32 * first;
+  int my = 0;
+  if (base + lane < ee) my = edge_col[base + lane] | (edge_tri[base + lane] ? (int)0x80000000 : 0);
+  while (base < ee) {
+    const int n = min(32, ee - base);
+    const int cur = my;
+    base += 32 * step;
+    my = 0;
+    if (base + lane < ee) my = edge_col[base + lane] | (edge_tri[base + lane] ? (int)0x80000000 : 0);
+    if (n <= 8) gather_chunk<4>(h, cur, n, half, l16, at, ad);
+    else if (n <= 16) gather_chunk<8>(h, cur, n, half, l16, at, ad);
+    else gather_chunk<16>(h, cur, n, half, l16, at, ad);
   }
+#define DESCO_XH(a) a += __shfl_xor_sync(FULL_MASK, a, 16)
+  DESCO_XH(at.x); DESCO_XH(at.y); DESCO_XH(at.z); DESCO_XH(at.w);
+  DESCO_XH(ad.x); DESCO_XH(ad.y); DESCO_XH(ad.z); DESCO_XH(ad.w);
+#undef DESCO_XH
 }
 
 // 4 consecutive features of row r as bf16 hi / lo, swizzled (8-byte stores; 16 lanes cover the 128-byte row)
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BARS);  // [0] weights, [1] MMA done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   int* s_nhub = reinterpret_cast<int*>(tmem_slot + 1);
+  int* s_ticket = s_nhub + 1;  // [2], by tile parity
   uint8_t* s_hubs = reinterpret_cast<uint8_t*>(bars) + 64;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -167,9 +169,10 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
       s_row[b * 5 * TR + tid] = row;
       s_g[b * 5 * TR + tid] = g;
       s_code[b * 5 * TR + tid] = code;
-      s_eb[b * 5 * TR + tid] = eb;
+      s_eb[b * 5 * TR + tid] = eb;  // fetched one tile ahead: a row's gather starts with its source words
       s_ee[b * 5 * TR + tid] = ee;
     }
+    if (tid == TR) s_ticket[b] = 0;
   };
   setup(blockIdx.x, 0);
   if (tid == 0) *s_nhub = 0;
@@ -183,51 +186,42 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
     const int* t_eb = s_eb + buf * 5 * TR;
     const int* t_ee = s_ee + buf * 5 * TR;
 
-    // ---- gather: [sum tri | sum tride | self] of every row -> bf16 hi/lo operand images.  Warp w walks the row pairs
-    //      (2w, 2w+1), (2w + 2 NW, ..): one row per half-warp; the edge ranges were fetched at set-up time and the next
-    //      pair's first source words load under the current pair's rows, so a short row costs ONE memory latency ----
-    {
-      int r = 2 * warp + half;
-      int eb = t_eb[r], ee = t_ee[r];
-      int cur = (eb + l16 < ee && ee - eb <= HUB_DEG) ? edge_word(p.edge_col, p.edge_tri, eb + l16) : 0;
+    // ---- gather: [sum tri | sum tride | self] of every row -> bf16 hi/lo operand images; rows are dealt by a ticket, so a
+    //      warp that drew a long row (or is still in the previous tile's epilogue) simply takes fewer of them ----
 #pragma unroll 1
-      for (; r < TR; r += 2 * NW) {
-        const int row = t_row[r];
-        const int rn = r + 2 * NW;
-        int ebn = 0, een = 0, curn = 0;
-        if (rn < TR) {
-          ebn = t_eb[rn]; een = t_ee[rn];
-          if (ebn + l16 < een && een - ebn <= HUB_DEG) curn = edge_word(p.edge_col, p.edge_tri, ebn + l16);
-        }
-        float4 at = make_float4(0.f, 0.f, 0.f, 0.f), ad = at, self = at;
-        if (row >= 0) self = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)row * F) + l16);
-        const bool hub = ee - eb > HUB_DEG;
-        if (hub && l16 == 0) s_hubs[atomicAdd(s_nhub, 1)] = (uint8_t)r;
-        gather_edges(p.h_in, p.edge_col, p.edge_tri, eb, hub ? eb : ee, 0, 1, l16, cur, at, ad);
-        if (!hub) {
-          store_quad(sA, r, l16, at);
-          store_quad(sA + 2 * IMG, r, l16, ad);
-        }
-        store_quad(sA + 4 * IMG, r, l16, self);
-        eb = ebn; ee = een; cur = curn;
+    for (;;) {
+      int r = 0;
+      if (lane == 0) r = atomicAdd(&s_ticket[buf], 1);
+      r = __shfl_sync(FULL_MASK, r, 0);
+      if (r >= TR) break;
+      const int row = t_row[r];
+      float4 at = make_float4(0.f, 0.f, 0.f, 0.f), ad = at, self = at;
+      bool hub = false;
+      if (row >= 0) {
+        if (half == 0) self = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)row * F) + l16);
+        const int eb = t_eb[r], ee = t_ee[r];
+        hub = ee - eb > HUB_DEG;
+        if (!hub) gather_edges(p.h_in, p.edge_col, p.edge_tri, eb, ee, 0, 1, lane, at, ad);
+        else if (lane == 0) s_hubs[atomicAdd(s_nhub, 1)] = (uint8_t)r;
       }
+      if (!hub) store_quad(sA + (half ? 2 * IMG : 0), r, l16, half ? ad : at);  // the two halves write one block each
+      if (half == 0) store_quad(sA + 4 * IMG, r, l16, self);
     }
     __syncthreads();  // every warp is past the previous tile's epilogue here: the other metadata buffer is free
     setup(tile + gridDim.x, buf ^ 1);
-    for (int hh = 0, nh = *s_nhub; hh < nh; ++hh) {  // hub rows: 16-edge chunks dealt over all half-warps, summed in order
+    for (int hh = 0, nh = *s_nhub; hh < nh; ++hh) {  // hub rows: 32-edge chunks dealt over all warps, summed in warp order
       const int r = s_hubs[hh], row = t_row[r];
-      (void)row;
-      const int eb = t_eb[r], ee = t_ee[r];
-      const int first = 2 * warp + half;
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f), ad = at;
-      const int cur = (eb + 16 * first + l16 < ee) ? edge_word(p.edge_col, p.edge_tri, eb + 16 * first + l16) : 0;
-      gather_edges(p.h_in, p.edge_col, p.edge_tri, eb, ee, first, 2 * NW, l16, cur, at, ad);
-      s_hub[(first * 16 + l16) * 2] = at;
-      s_hub[(first * 16 + l16) * 2 + 1] = ad;
+      (void)row;
+      gather_edges(p.h_in, p.edge_col, p.edge_tri, t_eb[r], t_ee[r], warp, NW, lane, at, ad);
+      if (half == 0) {
+        s_hub[(warp * 16 + l16) * 2] = at;
+        s_hub[(warp * 16 + l16) * 2 + 1] = ad;
+      }
       __syncthreads();
       if (warp == 0) {
         float4 t = s_hub[l16 * 2 + half];  // half 0 sums the triangle partials, half 1 the tride partials
-        for (int w = 1; w < 2 * NW; ++w) add4(t, s_hub[(w * 16 + l16) * 2 + half]);
+        for (int w = 1; w < NW; ++w) add4(t, s_hub[(w * 16 + l16) * 2 + half]);
         store_quad(sA + (half ? 2 * IMG : 0), r, l16, t);
       }
       __syncthreads();
