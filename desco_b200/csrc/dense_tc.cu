@@ -23,6 +23,7 @@ constexpr int A_BYTES = TM * 128;  // one bf16 image of a 128 x 64 atom
 
 struct DenseArgs {
   const float* X; int ldx;
+  const uint8_t* Ximg;   // [row block][k_atom][hi | mid | lo] A operand images, or NULL (then X is converted here)
   const uint8_t* Wimg;   // [n_block][k_atom][hi | mid | lo], each image nblk * 128 bytes
   const float* bias;     // [N] or NULL
   const float* R; int ldr;  // residual added AFTER the activation, or NULL
@@ -60,10 +61,15 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
   bool timed_out = false;
 
   auto stage_ptr = [&](int s) { return smem + s * stage_bytes; };
-  auto issue_b = [&](int a) {  // thread 0: weight images of atom a -> stage a & 1
+  const bool a_img = p.Ximg != nullptr;
+  auto issue_b = [&](int a) {  // thread 0: weight images (and, when given, the A images) of atom a -> stage a & 1
     uint8_t* st = stage_ptr(a & 1);
-    tc05::mbar_arrive_expect_tx(&bars[a & 1], 3 * b_bytes);
+    tc05::mbar_arrive_expect_tx(&bars[a & 1], 3 * b_bytes + (a_img ? 3 * A_BYTES : 0));
     tc05::bulk_g2s(st + 3 * A_BYTES, wbase + (size_t)a * 3 * b_bytes, 3 * b_bytes, &bars[a & 1]);
+    if (a_img) {
+      const uint8_t* src = p.Ximg + ((size_t)blockIdx.x * KA + a) * (3 * A_BYTES);
+      for (int part = 0; part < 3; ++part) tc05::bulk_g2s(st + part * A_BYTES, src + part * A_BYTES, A_BYTES, &bars[a & 1]);
+    }
   };
   if (tid == 0) issue_b(0);
 
@@ -77,17 +83,18 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
       if (m0 + r < p.M) dst[it] = __ldg(reinterpret_cast<const float4*>(p.X + (size_t)(m0 + r) * p.ldx + 64 * a + 4 * hl));
     }
   };
-  load_x(0, xin);
+  if (!a_img) load_x(0, xin);
 
   for (int a = 0; a < KA; ++a) {
     const int s = a & 1;
     if (a + 1 < KA) {  // free the other stage (read by the MMAs of atom a-1) and start fetching atom a+1's weights
-      load_x(a + 1, xnext);  // ... and atom a+1 of X: in flight while atom a is converted and multiplied
+      if (!a_img) load_x(a + 1, xnext);  // ... and atom a+1 of X: in flight while atom a is converted and multiplied
       if (a >= 1 && !tc05::mbar_wait(&bars[2 + (s ^ 1)], ((a - 1) >> 1) & 1)) timed_out = true;
       if (tid == 0) issue_b(a + 1);
     }
     // X[m0 .. m0+127][64 a .. 64 a + 63] -> bf16 hi / mid / lo swizzled images (one half-warp per row)
     uint8_t* sA = stage_ptr(s);  // hi | mid | lo images of the A atom, then hi | mid | lo of the B atom
+    if (!a_img) {
 #pragma unroll
     for (int it = 0; it < ROWS_PER_THREAD; ++it) {
       const int r = warp * 2 + hw + it * (THREADS / 16);
@@ -110,6 +117,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
     for (int it = 0; it < ROWS_PER_THREAD; ++it) xin[it] = xnext[it];
     tc05::fence_proxy_async_smem();
     __syncthreads();
+    }
     if (tid == 0) {
       if (!tc05::mbar_wait(&bars[s], (a >> 1) & 1)) timed_out = true;
       tc05::fence_after_sync();
@@ -173,9 +181,9 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
 
 }  // namespace
 
-int desco_internal_dense_tc(const float* X, int ldx, const void* Wimg, const float* bias, const float* R, int ldr, float* Y,
-                            int ldy, int M, int K, int N, int nblk, int act, float slope, int passes, int32_t* status,
-                            cudaStream_t s) {
+int desco_internal_dense_tc(const float* X, const void* Ximg, int ldx, const void* Wimg, const float* bias, const float* R,
+                            int ldr, float* Y, int ldy, int M, int K, int N, int nblk, int act, float slope, int passes,
+                            int32_t* status, cudaStream_t s) {
   if (M == 0) return DESCO_OK;
   if (K % 64 || nblk % 16 || nblk > 160 || N % nblk || passes < 1 || passes > 6 || !status) return DESCO_EINVAL;
   const size_t smem = 1024 + 2 * (size_t)(3 * A_BYTES + 3 * nblk * 128) + 64;
@@ -185,7 +193,7 @@ int desco_internal_dense_tc(const float* X, int ldx, const void* Wimg, const flo
     attr = smem;
   }
   DenseArgs a;
-  a.X = X; a.ldx = ldx; a.Wimg = (const uint8_t*)Wimg; a.bias = bias; a.R = R; a.ldr = ldr; a.Y = Y; a.ldy = ldy;
+  a.X = X; a.Ximg = (const uint8_t*)Ximg; a.ldx = ldx; a.Wimg = (const uint8_t*)Wimg; a.bias = bias; a.R = R; a.ldr = ldr; a.Y = Y; a.ldy = ldy;
   a.M = M; a.K = K; a.nblk = nblk; a.act = act; a.passes = passes; a.slope = slope; a.status = status;
   dim3 grid((M + TM - 1) / TM, N / nblk);
   DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);

@@ -381,6 +381,7 @@ struct Workspace {
   int32_t* row_nbh; int32_t* crow; uint8_t* canon_code; int32_t* quirk_row;
   float *hA, *hB, *emb_a, *pool, *cvec, *z, *t1, *t2, *t3;
   void* fused;  // tile plan of the fused tcgen05 path
+  void* emb_img;  // canonical rows of all layers as A operand images of the anchor GEMM (fused path)
   void* mt;     // pooling partials of the multi-tile tcgen05 path
   size_t bytes;
 };
@@ -404,6 +405,7 @@ Workspace carve(void* base, int V, int G, int layers) {
   w.t2 = (float*)take((size_t)G * F * 4);
   w.t3 = (float*)take((size_t)G * 4 * F * 4);
   w.fused = (void*)take((size_t)desco_internal_shmp_fused_workspace_bytes(G));
+  w.emb_img = (void*)take((size_t)((G + 127) / 128) * (layers + 1) * 3 * 128 * 128);
   w.mt = (void*)take((size_t)desco_internal_shmp_mt_workspace_bytes(V, G));
   w.bytes = off;
   return w;
@@ -450,7 +452,7 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
   if (fused) {
     const int rc = desco_internal_shmp_fused_layers(nbh_ptr, edge_ptr, edge_col, edge_tri, G, pyg_batch_size, feat, input_dim,
                                                     w_pre, w_layers_tc, layers, precision == DESCO_PRECISION_BF16X3 ? 3 : 1,
-                                                    ws.emb_a, ws.pool, emb_ld, ws.fused, status, s);
+                                                    ws.emb_a, ws.emb_img, ws.pool, emb_ld, ws.fused, status, s);
     if (rc) return rc;
   } else {
   {
@@ -535,7 +537,9 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
     // 144-column blocks: 576 / 144 = 4 column blocks x 32 row blocks = 128 CTAs for 4096 neighborhoods, one wave on 148 SMs
     // (96-column blocks were 192 CTAs = two waves)
     if (emb_ld % 144) return DESCO_EINVAL;
-    if ((rc = desco_internal_dense_tc(ws.emb_a, emb_ld, iWanc, banc, ws.pool, emb_ld, ws.z, emb_ld, G, emb_ld, emb_ld, 144, 2, 0.1f, passes, status, s))) return rc;
+    // (the fused kernel leaves the canonical rows as ready-made A operand images; the multi-tile path as fp32 rows)
+    if ((rc = desco_internal_dense_tc(ws.emb_a, fused ? ws.emb_img : nullptr, emb_ld, iWanc, banc, ws.pool, emb_ld, ws.z, emb_ld,
+                                      G, emb_ld, emb_ld, 144, 2, 0.1f, passes, status, s))) return rc;
     return desco_internal_readout_chain(ws.z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, s);
   }
   if (hetero) {  // z = pool_count + LeakyReLU_0.1(anchor(emb_canonical))  (gnn_model.py:69-73, 88-89, 107)
@@ -599,8 +603,8 @@ int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const f
     const int passes = precision == DESCO_PRECISION_BF16X3 ? 6 : 1;
     const uint8_t* iW1a = (const uint8_t*)w_head_tc;
     const uint8_t* iW1b = iW1a + (size_t)F * HEAD_H * 6;
-    if ((rc = desco_internal_dense_tc(emb_target, F, iW1a, nullptr, nullptr, 0, T, HEAD_H, G, F, HEAD_H, 128, 0, 0.f, passes, status, s))) return rc;
-    if ((rc = desco_internal_dense_tc(emb_query, F, iW1b, b1, nullptr, 0, Bq, HEAD_H, Q, F, HEAD_H, 128, 0, 0.f, passes, status, s))) return rc;
+    if ((rc = desco_internal_dense_tc(emb_target, nullptr, F, iW1a, nullptr, nullptr, 0, T, HEAD_H, G, F, HEAD_H, 128, 0, 0.f, passes, status, s))) return rc;
+    if ((rc = desco_internal_dense_tc(emb_query, nullptr, F, iW1b, b1, nullptr, 0, Bq, HEAD_H, Q, F, HEAD_H, 128, 0, 0.f, passes, status, s))) return rc;
   } else {
   if ((rc = dense(emb_target, F, W1a, nullptr, nullptr, 0, T, HEAD_H, G, F, HEAD_H, ACT_NONE, 0.f, s))) return rc;
   if ((rc = dense(emb_query, F, W1b, b1, nullptr, 0, Bq, HEAD_H, Q, F, HEAD_H, ACT_NONE, 0.f, s))) return rc;

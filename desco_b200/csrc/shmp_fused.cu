@@ -142,6 +142,8 @@ struct FusedArgs {
   const float* w_pre;       // per node type (count, canonical): W[input_dim][64], b[64]
   const uint8_t* w_layers;  // layers x LAYER_BYTES
   float* emb_a;             // [G][emb_ld] canonical rows, all layers
+  uint8_t* emb_img;         // the same rows as ready-made tensor-core A operands of the anchor GEMM (or NULL): per block of
+                            // 128 neighborhoods and layer one 64-wide K atom, bf16 hi | mid | lo SWIZZLE_128B images
   float* pool;              // [G][emb_ld] sum over count rows, all layers
   int32_t* status;
 };
@@ -391,7 +393,18 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
             const size_t gofs = (size_t)(nb0 + i) * p.emb_ld + (size_t)l * F + f;
             p.pool[gofs] = (s0 + s1) + (s2 + s3);          // global_add_pool, count rows (gnn_model.py:107)
             const float ha = sCh[i * F + f];
-            p.emb_a[gofs] = ha;                            // skip-concat of the canonical row (:275)
+            if (p.emb_img) {  // skip-concat of the canonical row (:275), split three ways for csrc/dense_tc.cu
+              const int g = nb0 + i;
+              uint8_t* img = p.emb_img + ((size_t)(g >> 7) * (p.layers + 1) + l) * (3 * TR * 128) + tc05::sw128_offset(g & 127, f);
+              const __nv_bfloat16 hi = __float2bfloat16_rn(ha);
+              const float r1 = ha - __bfloat162float(hi);
+              const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+              *reinterpret_cast<__nv_bfloat16*>(img) = hi;
+              *reinterpret_cast<__nv_bfloat16*>(img + TR * 128) = mid;
+              *reinterpret_cast<__nv_bfloat16*>(img + 2 * TR * 128) = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+            } else {
+              p.emb_a[gofs] = ha;
+            }
             if (l < p.layers) {
               float vt = 0.f, vd = 0.f;
               const int quirk = sQuirk[i];
@@ -594,7 +607,8 @@ int64_t desco_internal_shmp_fused_workspace_bytes(int num_neighborhoods) {
 int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col,
                                      const uint8_t* edge_tri, int G, int pyg_batch_size, const float* feat, int input_dim,
                                      const float* w_pre, const void* w_layers_tc, int layers, int passes, float* emb_a,
-                                     float* pool, int emb_ld, void* workspace, int32_t* status, cudaStream_t s) {
+                                     void* emb_img, float* pool, int emb_ld, void* workspace, int32_t* status,
+                                     cudaStream_t s) {
   if (G <= 0) return DESCO_OK;
   if (!status || !workspace || !w_layers_tc) return DESCO_EINVAL;
   const int chunks = (G + CH - 1) / CH;
@@ -616,7 +630,7 @@ int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge
   a.tile_start = tile_start; a.tile_count = tile_count; a.ticket = ticket;
   a.G = G; a.num_chunks = chunks; a.pyg_batch_size = pyg_batch_size; a.layers = layers; a.passes = passes;
   a.input_dim = input_dim; a.emb_ld = emb_ld;
-  a.feat = feat; a.w_pre = w_pre; a.w_layers = (const uint8_t*)w_layers_tc; a.emb_a = emb_a; a.pool = pool; a.status = status;
+  a.feat = feat; a.w_pre = w_pre; a.w_layers = (const uint8_t*)w_layers_tc; a.emb_a = emb_a; a.emb_img = (uint8_t*)emb_img; a.pool = pool; a.status = status;
   {
     DescoProfScope prof(DESCO_PROF_SHMP_LAYER, s);
     shmp_fused_kernel<<<desco_num_sms(), THREADS, SMEM_BYTES, s>>>(a);

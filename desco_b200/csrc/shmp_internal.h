@@ -19,10 +19,13 @@ int64_t desco_internal_shmp_fused_workspace_bytes(int num_neighborhoods);
 int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col,
                                      const uint8_t* edge_tri, int G, int pyg_batch_size, const float* feat, int input_dim,
                                      const float* w_pre, const void* w_layers_tc, int layers, int passes, float* emb_a,
-                                     float* pool, int emb_ld, void* workspace, int32_t* status, cudaStream_t s);
+                                     void* emb_img, float* pool, int emb_ld, void* workspace, int32_t* status,
+                                     cudaStream_t s);
 
 // Y = act(X . W^T + b) (+ R) on tcgen05 (csrc/dense_tc.cu).  Wimg: pack_dense_tc images; act: 0 none, 1 relu, 2 leaky.
-int desco_internal_dense_tc(const float* X, int ldx, const void* Wimg, const float* bias, const float* R, int ldr, float* Y,
+// Ximg != NULL: X comes as ready-made operand images (per block of 128 rows and 64-wide K atom: bf16 hi | mid | lo
+// SWIZZLE_128B images, 3 x 16 KB) and is fetched by bulk async copy instead of being converted by the threads.
+int desco_internal_dense_tc(const float* X, const void* Ximg, int ldx, const void* Wimg, const float* bias, const float* R, int ldr, float* Y,
                             int ldy, int M, int K, int N, int nblk, int act, float slope, int passes, int32_t* status,
                             cudaStream_t s);
 

@@ -226,13 +226,14 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
       }
       __syncthreads();
     }
-    if (tid == 0) *s_nhub = 0;  // (the next tile's gather pushes its hubs only after the barrier below)
     tc05::fence_proxy_async_smem();
     tc05::fence_before_sync();
     __syncthreads();
 
     // ---- [128 x 192] . [192 x 64] on tcgen05: hi.hi + lo.hi + hi.lo ----
     if (tid == 0) {
+      *s_nhub = 0;  // every thread has read the hub count (barrier above); the next tile's gather, which pushes its hubs,
+                    // starts only after the MMA issued below has completed
       if (!weights_ready) {
         if (!tc05::mbar_wait(&bars[0], 0)) { atomicExch(p.status, DESCO_ECUDA); __trap(); }
         weights_ready = true;
