@@ -91,6 +91,7 @@ SIGNATURES = {
     "desco_partition_fill": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "desco_partition_batch_workspace_bytes": (_L, [_I]),
     "desco_partition_batch": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _L, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP, _VP, _L, _VP, _VP]),
+    "desco_partition_batch_async": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _L, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP, _VP, _L, _VP, _VP]),
     "desco_partition_large_workspace_bytes": (_L, [_I, _I]),
     "desco_partition_large_count": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
     "desco_partition_large_fill": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _L, _VP]),
@@ -101,6 +102,8 @@ SIGNATURES = {
     "desco_shmp_layer_weight_floats": (_L, []),
     "desco_shmp_tc_layer_bytes": (_L, []),
     "desco_shmp_forward": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _L, _I, _VP, _VP]),
+    "desco_shmp_forward_dev": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP, _I, _VP, _I, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _L, _I, _VP, _VP]),
+    "desco_count_head_dev": (_I, [_VP, _I, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _L, _VP]),
     "desco_shmp_mt_layer_bytes": (_L, []),
     "desco_shmp_forward_mt": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _L, _I, _VP, _VP]),
     "desco_count_head_workspace_bytes": (_L, [_I, _I]),

@@ -31,6 +31,7 @@ struct DenseArgs {
   int M, K, nblk, act, passes;
   float slope;
   int32_t* status;
+  const int32_t* m_dev;  // device-resident row count (stream-ordered form; M is then the capacity) or NULL
 };
 
 __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p) {
@@ -44,6 +45,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hw = lane >> 4, hl = lane & 15;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * p.nblk;
+  const int M = p.m_dev ? min(p.M, *p.m_dev) : p.M;
+  if (m0 >= M) return;  // (whole CTA, before any barrier / TMEM allocation)
   const int KA = p.K / 64;
   const uint32_t tmem_cols = p.nblk <= 32 ? 32 : p.nblk <= 64 ? 64 : p.nblk <= 128 ? 128 : 256;
 
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
     for (int it = 0; it < ROWS_PER_THREAD; ++it) {
       const int r = warp * 2 + hw + it * (THREADS / 16);
       dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + r < p.M) dst[it] = __ldg(reinterpret_cast<const float4*>(p.X + (size_t)(m0 + r) * p.ldx + 64 * a + 4 * hl));
+      if (m0 + r < M) dst[it] = __ldg(reinterpret_cast<const float4*>(p.X + (size_t)(m0 + r) * p.ldx + 64 * a + 4 * hl));
     }
   };
   if (!a_img) load_x(0, xin);
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
     for (int c = half * cols_per_half; c < (half + 1) * cols_per_half && c < p.nblk; c += 16) {
       float v[16];
       tc05::tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + c, v);
-      if (r < p.M) {
+      if (r < M) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           if (c + i >= p.nblk) break;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const DenseArgs p)
 
 int desco_internal_dense_tc(const float* X, const void* Ximg, int ldx, const void* Wimg, const float* bias, const float* R,
                             int ldr, float* Y, int ldy, int M, int K, int N, int nblk, int act, float slope, int passes,
-                            int32_t* status, cudaStream_t s) {
+                            int32_t* status, const int32_t* m_dev, cudaStream_t s) {
   if (M == 0) return DESCO_OK;
   if (K % 64 || nblk % 16 || nblk > 160 || N % nblk || passes < 1 || passes > 6 || !status) return DESCO_EINVAL;
   const size_t smem = 1024 + 2 * (size_t)(3 * A_BYTES + 3 * nblk * 128) + 64;
@@ -194,7 +197,7 @@ int desco_internal_dense_tc(const float* X, const void* Ximg, int ldx, const voi
   }
   DenseArgs a;
   a.X = X; a.Ximg = (const uint8_t*)Ximg; a.ldx = ldx; a.Wimg = (const uint8_t*)Wimg; a.bias = bias; a.R = R; a.ldr = ldr; a.Y = Y; a.ldy = ldy;
-  a.M = M; a.K = K; a.nblk = nblk; a.act = act; a.passes = passes; a.slope = slope; a.status = status;
+  a.M = M; a.K = K; a.nblk = nblk; a.act = act; a.passes = passes; a.slope = slope; a.status = status; a.m_dev = m_dev;
   dim3 grid((M + TM - 1) / TM, N / nblk);
   DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
   dense_tc_kernel<<<grid, THREADS, smem, s>>>(a);

@@ -1829,6 +1829,76 @@ int desco_partition_batch(const int32_t* rowptr, const int32_t* col, const int32
                           centre_graph, 1, noff, eoff, node_gid, edge_ptr, edge_col, edge_tri, small + 4, s);
 }
 
+}  // extern "C"
+
+namespace {
+// Capacity guard of the stream-ordered (no host sync) form: when the exact row / edge totals do not fit the caller's
+// buffers, every neighborhood is marked dropped (the fill pass skips them), the effective sizes become 0 and the status
+// word reports ENOBUFS / ERANGE.  small: [0..3] totals of the scan, [4] status, [8..11] exact 64-bit sums,
+// [12..15] effective {G, V, E, max rows} that every later kernel of the step reads.
+__global__ void partition_guard_kernel(int32_t* __restrict__ ne, int C, int32_t* __restrict__ small, long long cap_rows,
+                                       long long cap_edges) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long* sums64 = reinterpret_cast<const unsigned long long*>(small + 8);
+  const bool range = sums64[0] > 0x7fffffffull || sums64[1] > 0x7fffffffull;
+  const bool over = range || (long long)sums64[0] > cap_rows || (long long)sums64[1] > cap_edges || small[4] != 0;
+  if (i < C && over) ne[i] = 0;
+  if (i == 0) {
+    if (over && small[4] == 0) small[4] = range ? DESCO_ERANGE : DESCO_ENOBUFS;
+    for (int k = 0; k < 4; ++k) small[12 + k] = over ? 0 : small[k];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int desco_partition_batch_async(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
+                                const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
+                                int32_t max_graph_nodes, void* workspace, int64_t workspace_bytes, int32_t* nbh_ptr,
+                                int32_t* centre_out, uint8_t* indicator, int32_t* centre_graph, int32_t* node_gid,
+                                int32_t* edge_ptr, int64_t cap_rows, int32_t* edge_col, uint8_t* edge_tri, int64_t cap_edges,
+                                int32_t* sizes_dev, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!sizes_dev || !nbh_ptr || num_centres <= 0 || cap_rows < 1 || cap_edges < 1) return DESCO_EINVAL;
+  if (!workspace || workspace_bytes < desco_partition_batch_workspace_bytes(num_centres) || !centre_out || !centre_graph ||
+      !node_gid || !edge_ptr || !edge_col || !edge_tri)
+    return DESCO_EINVAL;
+  const size_t c = (size_t)num_centres;
+  int32_t* nv = (int32_t*)workspace;
+  int32_t* ne = nv + c;
+  int32_t* rank = ne + c;
+  int32_t* noff = rank + c;
+  int32_t* eoff = noff + c;
+  void* scan_ws = (char*)workspace + ((5 * c * 4 + 255) / 256) * 256 + 256;
+  const int64_t scan_bytes = desco_partition_scan_workspace_bytes(num_centres);
+  int32_t* small = sizes_dev;
+  DESCO_CUDA_TRY(cudaMemsetAsync(small, 0, 16 * sizeof(int32_t), s));
+  DESCO_CUDA_TRY(cudaMemsetAsync(edge_ptr, 0, sizeof(int32_t), s));
+  int rc = launch_partition(rowptr, col, graph_ptr, num_graphs, centres, num_centres, depth, mode, max_graph_nodes, nv, ne,
+                            centre_graph, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, small + 4, s);
+  if (rc) return rc;
+  desco_count_launches(2);
+  if (num_centres <= 65536) {
+    scan_small_kernel<<<1, 1024, 0, s>>>(centres, nv, ne, num_centres, noff, eoff, nbh_ptr, centre_out, indicator, small);
+  } else {
+    size_t bytes = (size_t)scan_bytes;
+    cub::TransformInputIterator<int, KeepFlag, const int32_t*> it(ne, KeepFlag());
+    DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_ws, bytes, it, rank, num_centres, s));
+    bytes = (size_t)scan_bytes;
+    DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_ws, bytes, nv, noff, num_centres, s));
+    bytes = (size_t)scan_bytes;
+    DESCO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_ws, bytes, ne, eoff, num_centres, s));
+    scan_finalize_kernel<<<(num_centres + 255) / 256, 256, 0, s>>>(centres, nv, ne, rank, noff, eoff, num_centres, nbh_ptr,
+                                                                  centre_out, indicator, small, small + 3,
+                                                                  reinterpret_cast<unsigned long long*>(small + 8));
+  }
+  partition_guard_kernel<<<(num_centres + 255) / 256, 256, 0, s>>>(ne, num_centres, small, (long long)cap_rows,
+                                                                  (long long)cap_edges);
+  DESCO_LAUNCH_CHECK();
+  return launch_partition(rowptr, col, graph_ptr, num_graphs, centres, num_centres, depth, mode, max_graph_nodes, nv, ne,
+                          centre_graph, 1, noff, eoff, node_gid, edge_ptr, edge_col, edge_tri, small + 4, s);
+}
+
 int desco_partition_fill(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
                          const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
                          int32_t max_graph_nodes, const int32_t* nv, const int32_t* ne, const int32_t* centre_graph,

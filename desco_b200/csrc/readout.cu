@@ -135,6 +135,7 @@ struct ChainArgs {
   const float* Z; int ldz; int K0; int G;        // [G][K0] pooled embedding (K0 = (layers + 1) * 64)
   const float *P0, *b0, *P1, *b1, *P2, *b2, *P3, *b3;  // row-major [in][out]
   float* out;                                    // [G][64]
+  const int32_t* g_dev;                          // device-resident G (stream-ordered form) or NULL
 };
 
 __global__ void __launch_bounds__(THREADS, 1) readout_chain_kernel(const ChainArgs p) {
@@ -147,12 +148,14 @@ __global__ void __launch_bounds__(THREADS, 1) readout_chain_kernel(const ChainAr
   float* sT3 = sT2 + ROWS * LD64;                // [ROWS][LD256]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g0 = blockIdx.x * ROWS;
+  const int G = p.g_dev ? min(p.G, *p.g_dev) : p.G;
+  if (g0 >= G) return;
 
   const int k4n = p.K0 / 4;
   for (int i = tid; i < ROWS * k4n; i += THREADS) {
     const int r = i / k4n, c4 = (i - r * k4n) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g0 + r < p.G) v = __ldg(reinterpret_cast<const float4*>(p.Z + (size_t)(g0 + r) * p.ldz + c4));
+    if (g0 + r < G) v = __ldg(reinterpret_cast<const float4*>(p.Z + (size_t)(g0 + r) * p.ldz + c4));
     *reinterpret_cast<float4*>(sX + r * ldx + c4) = v;
   }
   __syncthreads();
@@ -192,17 +195,17 @@ __global__ void __launch_bounds__(THREADS, 1) readout_chain_kernel(const ChainAr
     }
   }
   __syncthreads();
-  reduce_partials<LD64>(sPart, p.b0, ACT_LEAKY, 0.1f, sT1, nullptr, g0, p.G, tid);   // Linear(576,64) + LeakyReLU(.1)
+  reduce_partials<LD64>(sPart, p.b0, ACT_LEAKY, 0.1f, sT1, nullptr, g0, G, tid);   // Linear(576,64) + LeakyReLU(.1)
   __syncthreads();
   splitk_gemm64<LD64>(sT1, F, p.P1, sPart, warp, lane);
   __syncthreads();
-  reduce_partials<LD64>(sPart, p.b1, ACT_RELU, 0.f, sT2, nullptr, g0, p.G, tid);      // Linear(64,64) + ReLU
+  reduce_partials<LD64>(sPart, p.b1, ACT_RELU, 0.f, sT2, nullptr, g0, G, tid);      // Linear(64,64) + ReLU
   __syncthreads();
   splitn_gemm256<LD64, LD256>(sT2, p.P2, p.b2, ACT_RELU, 0.f, sT3, warp, lane);       // Linear(64,256) + ReLU
   __syncthreads();
   splitk_gemm64<LD256>(sT3, H4, p.P3, sPart, warp, lane);
   __syncthreads();
-  reduce_partials<LD64>(sPart, p.b3, ACT_NONE, 0.f, nullptr, p.out, g0, p.G, tid);    // Linear(256,64)
+  reduce_partials<LD64>(sPart, p.b3, ACT_NONE, 0.f, nullptr, p.out, g0, G, tid);    // Linear(256,64)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -214,6 +217,7 @@ struct HeadArgs {
   const float *W1a, *W1b, *b1, *w2, *b2;  // [64][256], [64][256], [256], [256], [1]
   float* pred;                  // [G][Q] or NULL
   float* count;                 // [G][Q] or NULL
+  const int32_t* g_dev;         // device-resident G (stream-ordered form) or NULL
 };
 
 __global__ void __launch_bounds__(THREADS, 1) count_head_fused_kernel(const HeadArgs p) {
@@ -225,10 +229,12 @@ __global__ void __launch_bounds__(THREADS, 1) count_head_fused_kernel(const Head
   float* sW2 = sB + ROWS * LD256;      // [256]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g0 = blockIdx.x * ROWS;
+  const int G = p.g_dev ? min(p.G, *p.g_dev) : p.G;
+  if (g0 >= G) return;
   for (int i = tid; i < ROWS * (F / 4); i += THREADS) {
     const int r = i >> 4, c4 = (i & 15) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), q = v;
-    if (g0 + r < p.G) v = __ldg(reinterpret_cast<const float4*>(p.emb_t + (size_t)(g0 + r) * F + c4));
+    if (g0 + r < G) v = __ldg(reinterpret_cast<const float4*>(p.emb_t + (size_t)(g0 + r) * F + c4));
     if (r < p.Q) q = __ldg(reinterpret_cast<const float4*>(p.emb_q + (size_t)r * F + c4));
     *reinterpret_cast<float4*>(sE + r * LD64 + c4) = v;
     *reinterpret_cast<float4*>(sQ + r * LD64 + c4) = q;
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_head_fused_kernel(const Head
       a0 = fmaf(v0, wv.x, a0); a1 = fmaf(v1, wv.y, a1); a2 = fmaf(v2, wv.z, a2); a3 = fmaf(v3, wv.w, a3);
     }
     const float acc = ((a0 + a1) + (a2 + a3)) + bias2;
-    if (g0 + r < p.G) {
+    if (g0 + r < G) {
       if (p.pred) p.pred[(size_t)(g0 + r) * p.Q + q] = acc;
       if (p.count) p.count[(size_t)(g0 + r) * p.Q + q] = exp2f(acc) - 1.f;  // 2**pred - 1 (lightning_model.py:221)
     }
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_head_fused_kernel(const Head
 
 int desco_internal_readout_chain(const float* Z, int ldz, int K0, int G, const float* P0, const float* b0, const float* P1,
                                  const float* b1, const float* P2, const float* b2, const float* P3, const float* b3,
-                                 float* out, cudaStream_t s) {
+                                 float* out, const int32_t* g_dev, cudaStream_t s) {
   if (G == 0) return DESCO_OK;
   if (K0 % 32 || K0 <= 0) return DESCO_EINVAL;
   const size_t smem = ((size_t)ROWS * (K0 + 4) + NW * ROWS * F + 2 * ROWS * LD64 + ROWS * LD256) * sizeof(float);
@@ -281,7 +287,7 @@ int desco_internal_readout_chain(const float* Z, int ldz, int K0, int G, const f
   }
   ChainArgs a;
   a.Z = Z; a.ldz = ldz; a.K0 = K0; a.G = G;
-  a.P0 = P0; a.b0 = b0; a.P1 = P1; a.b1 = b1; a.P2 = P2; a.b2 = b2; a.P3 = P3; a.b3 = b3; a.out = out;
+  a.P0 = P0; a.b0 = b0; a.P1 = P1; a.b1 = b1; a.P2 = P2; a.b2 = b2; a.P3 = P3; a.b3 = b3; a.out = out; a.g_dev = g_dev;
   DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
   readout_chain_kernel<<<(G + ROWS - 1) / ROWS, THREADS, smem, s>>>(a);
   DESCO_LAUNCH_CHECK();
@@ -290,7 +296,7 @@ int desco_internal_readout_chain(const float* Z, int ldz, int K0, int G, const f
 
 int desco_internal_count_head_fused(const float* emb_t, int G, const float* emb_q, int Q, const float* W1a, const float* W1b,
                                     const float* b1, const float* w2, const float* b2, float* pred, float* count,
-                                    cudaStream_t s) {
+                                    const int32_t* g_dev, cudaStream_t s) {
   if (G == 0 || Q == 0) return DESCO_OK;
   if (Q > ROWS) return DESCO_ERANGE;
   const size_t smem = ((size_t)2 * ROWS * LD64 + 2 * ROWS * LD256 + H4) * sizeof(float);
@@ -301,7 +307,7 @@ int desco_internal_count_head_fused(const float* emb_t, int G, const float* emb_
   }
   HeadArgs a;
   a.emb_t = emb_t; a.G = G; a.emb_q = emb_q; a.Q = Q;
-  a.W1a = W1a; a.W1b = W1b; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.pred = pred; a.count = count;
+  a.W1a = W1a; a.W1b = W1b; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.pred = pred; a.count = count; a.g_dev = g_dev;
   DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
   count_head_fused_kernel<<<(G + ROWS - 1) / ROWS, THREADS, smem, s>>>(a);
   DESCO_LAUNCH_CHECK();

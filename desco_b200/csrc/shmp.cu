@@ -432,7 +432,10 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
                              const float* feat, int32_t input_dim, const float* w_pre, const float* w_layers,
                              const void* w_layers_tc, const void* w_layers_mt, const float* w_readout,
                              const void* w_readout_tc, int32_t layers, int32_t hidden, float* out_emb, void* workspace,
-                             int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream) {
+                             int64_t workspace_bytes, int32_t precision, int32_t* status, const int32_t* sizes_dev,
+                             void* stream) {
+  // sizes_dev != NULL: the stream-ordered form - num_neighborhoods / num_rows are CAPACITIES and the batch's own
+  // {G, V, E, max rows} are read on the device (fused tensor-core path only)
   const int G = num_neighborhoods, V = num_rows;
   if (hidden != F || layers < 1 || input_dim < 1 || G < 0 || V < 0) return DESCO_EINVAL;
   if (precision < DESCO_PRECISION_FP32 || precision > DESCO_PRECISION_BF16) return DESCO_EINVAL;
@@ -442,6 +445,7 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
   const bool fused = !mt && precision != DESCO_PRECISION_FP32;
   if (fused && (!hetero || !w_layers_tc || !w_readout_tc || !status)) return DESCO_EINVAL;  // tensor-core path: count/canonical batches
   if (mt && (!w_layers || !status || (hetero && !w_readout_tc))) return DESCO_EINVAL;
+  if (sizes_dev && !fused) return DESCO_EINVAL;
   if (!fused && !w_layers) return DESCO_EINVAL;
   Workspace ws = carve(workspace, V, G, layers);
   if ((int64_t)ws.bytes > workspace_bytes) return DESCO_ENOMEM;
@@ -452,7 +456,7 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
   if (fused) {
     const int rc = desco_internal_shmp_fused_layers(nbh_ptr, edge_ptr, edge_col, edge_tri, G, pyg_batch_size, feat, input_dim,
                                                     w_pre, w_layers_tc, layers, precision == DESCO_PRECISION_BF16X3 ? 3 : 1,
-                                                    ws.emb_a, ws.emb_img, ws.pool, emb_ld, ws.fused, status, s);
+                                                    ws.emb_a, ws.emb_img, ws.pool, emb_ld, ws.fused, status, sizes_dev, s);
     if (rc) return rc;
   } else {
   {
@@ -539,8 +543,8 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
     if (emb_ld % 144) return DESCO_EINVAL;
     // (the fused kernel leaves the canonical rows as ready-made A operand images; the multi-tile path as fp32 rows)
     if ((rc = desco_internal_dense_tc(ws.emb_a, fused ? ws.emb_img : nullptr, emb_ld, iWanc, banc, ws.pool, emb_ld, ws.z, emb_ld,
-                                      G, emb_ld, emb_ld, 144, 2, 0.1f, passes, status, s))) return rc;
-    return desco_internal_readout_chain(ws.z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, s);
+                                      G, emb_ld, emb_ld, 144, 2, 0.1f, passes, status, sizes_dev, s))) return rc;
+    return desco_internal_readout_chain(ws.z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, sizes_dev, s);
   }
   if (hetero) {  // z = pool_count + LeakyReLU_0.1(anchor(emb_canonical))  (gnn_model.py:69-73, 88-89, 107)
     rc = dense(ws.emb_a, emb_ld, Wanc, banc, ws.pool, emb_ld, ws.z, emb_ld, G, emb_ld, emb_ld, ACT_LEAKY, 0.1f, s);
@@ -548,7 +552,7 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
     z = ws.z;
   }
   // post_mp (gnn_model.py:44-53)
-  return desco_internal_readout_chain(z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, s);
+  return desco_internal_readout_chain(z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, nullptr, s);
 }
 
 int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
@@ -559,7 +563,18 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
                        int32_t* status, void* stream) {
   return shmp_forward_impl(nbh_ptr, edge_ptr, edge_col, edge_tri, num_neighborhoods, num_rows, hetero, pyg_batch_size, feat,
                            input_dim, w_pre, w_layers, w_layers_tc, nullptr, w_readout, w_readout_tc, layers, hidden, out_emb,
-                           workspace, workspace_bytes, precision, status, stream);
+                           workspace, workspace_bytes, precision, status, nullptr, stream);
+}
+
+int desco_shmp_forward_dev(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
+                           int32_t cap_neighborhoods, int32_t cap_rows, const int32_t* sizes_dev, int32_t pyg_batch_size,
+                           const float* feat, int32_t input_dim, const float* w_pre, const void* w_layers_tc,
+                           const float* w_readout, const void* w_readout_tc, int32_t layers, int32_t hidden, float* out_emb,
+                           void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream) {
+  if (!sizes_dev || precision == DESCO_PRECISION_FP32) return DESCO_EINVAL;
+  return shmp_forward_impl(nbh_ptr, edge_ptr, edge_col, edge_tri, cap_neighborhoods, cap_rows, 1, pyg_batch_size, feat,
+                           input_dim, w_pre, nullptr, w_layers_tc, nullptr, w_readout, w_readout_tc, layers, hidden, out_emb,
+                           workspace, workspace_bytes, precision, status, sizes_dev, stream);
 }
 
 int desco_shmp_forward_mt(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
@@ -571,17 +586,19 @@ int desco_shmp_forward_mt(const int32_t* nbh_ptr, const int32_t* edge_ptr, const
   if (!w_layers_mt || precision == DESCO_PRECISION_FP32) return DESCO_EINVAL;
   return shmp_forward_impl(nbh_ptr, edge_ptr, edge_col, edge_tri, num_neighborhoods, num_rows, hetero, pyg_batch_size, feat,
                            input_dim, w_pre, w_layers, nullptr, w_layers_mt, w_readout, w_readout_tc, layers, hidden, out_emb,
-                           workspace, workspace_bytes, precision, status, stream);
+                           workspace, workspace_bytes, precision, status, nullptr, stream);
 }
 
 int64_t desco_count_head_workspace_bytes(int32_t num_neighborhoods, int32_t num_queries) {
   return (int64_t)(align_up((size_t)num_neighborhoods * HEAD_H * 4) + align_up((size_t)num_queries * HEAD_H * 4));
 }
 
-int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const float* emb_query, int32_t num_queries,
-                     const float* w_head, const void* w_head_tc, int32_t hidden, float* out_pred, float* out_count,
-                     void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream) {
+static int count_head_impl(const float* emb_target, int32_t num_neighborhoods, const float* emb_query, int32_t num_queries,
+                           const float* w_head, const void* w_head_tc, int32_t hidden, float* out_pred, float* out_count,
+                           void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status,
+                           const int32_t* g_dev, void* stream) {
   const int G = num_neighborhoods, Q = num_queries;
+  if (g_dev && Q > 32) return DESCO_ERANGE;  // the stream-ordered form serves the one-launch head
   if (hidden != F || G < 0 || Q < 0) return DESCO_EINVAL;
   if (G == 0 || Q == 0) return DESCO_OK;
   if (!emb_target || !emb_query || !w_head || !workspace || (!out_pred && !out_count)) return DESCO_EINVAL;
@@ -596,15 +613,15 @@ int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const f
   const float* w2 = b1 + HEAD_H;
   const float* b2 = w2 + HEAD_H;
   if (Q <= 32)  // one fused launch (csrc/readout.cu); the multi-launch path below serves larger query sets
-    return desco_internal_count_head_fused(emb_target, G, emb_query, Q, W1a, W1b, b1, w2, b2, out_pred, out_count, s);
+    return desco_internal_count_head_fused(emb_target, G, emb_query, Q, W1a, W1b, b1, w2, b2, out_pred, out_count, g_dev, s);
   int rc;
   if (precision != DESCO_PRECISION_FP32) {
     if (!w_head_tc || !status) return DESCO_EINVAL;
     const int passes = precision == DESCO_PRECISION_BF16X3 ? 6 : 1;
     const uint8_t* iW1a = (const uint8_t*)w_head_tc;
     const uint8_t* iW1b = iW1a + (size_t)F * HEAD_H * 6;
-    if ((rc = desco_internal_dense_tc(emb_target, nullptr, F, iW1a, nullptr, nullptr, 0, T, HEAD_H, G, F, HEAD_H, 128, 0, 0.f, passes, status, s))) return rc;
-    if ((rc = desco_internal_dense_tc(emb_query, nullptr, F, iW1b, b1, nullptr, 0, Bq, HEAD_H, Q, F, HEAD_H, 128, 0, 0.f, passes, status, s))) return rc;
+    if ((rc = desco_internal_dense_tc(emb_target, nullptr, F, iW1a, nullptr, nullptr, 0, T, HEAD_H, G, F, HEAD_H, 128, 0, 0.f, passes, status, nullptr, s))) return rc;
+    if ((rc = desco_internal_dense_tc(emb_query, nullptr, F, iW1b, b1, nullptr, 0, Bq, HEAD_H, Q, F, HEAD_H, 128, 0, 0.f, passes, status, nullptr, s))) return rc;
   } else {
   if ((rc = dense(emb_target, F, W1a, nullptr, nullptr, 0, T, HEAD_H, G, F, HEAD_H, ACT_NONE, 0.f, s))) return rc;
   if ((rc = dense(emb_query, F, W1b, b1, nullptr, 0, Bq, HEAD_H, Q, F, HEAD_H, ACT_NONE, 0.f, s))) return rc;
@@ -616,6 +633,21 @@ int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const f
   count_head_kernel<<<(G + HEAD_TG - 1) / HEAD_TG, THREADS, smem, s>>>(T, Bq, w2, b2, G, Q, out_pred, out_count);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;
+}
+
+int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const float* emb_query, int32_t num_queries,
+                     const float* w_head, const void* w_head_tc, int32_t hidden, float* out_pred, float* out_count,
+                     void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream) {
+  return count_head_impl(emb_target, num_neighborhoods, emb_query, num_queries, w_head, w_head_tc, hidden, out_pred, out_count,
+                         workspace, workspace_bytes, precision, status, nullptr, stream);
+}
+
+int desco_count_head_dev(const float* emb_target, int32_t cap_neighborhoods, const int32_t* sizes_dev, const float* emb_query,
+                         int32_t num_queries, const float* w_head, int32_t hidden, float* out_pred, float* out_count,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!sizes_dev) return DESCO_EINVAL;
+  return count_head_impl(emb_target, cap_neighborhoods, emb_query, num_queries, w_head, nullptr, hidden, out_pred, out_count,
+                         workspace, workspace_bytes, DESCO_PRECISION_FP32, nullptr, sizes_dev, stream);
 }
 
 }  // extern "C"

@@ -78,6 +78,7 @@ static_assert(SM_AHI % 1024 == 0 && SM_ALO % 1024 == 0 && SM_BLO % 1024 == 0, "U
 // CH neighborhoods, by pointer doubling over jump[g] = first neighborhood of the tile after the one starting at g.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) shmp_tile_plan_kernel(const int32_t* __restrict__ nbh_ptr, int G,
+                                                              const int32_t* __restrict__ g_dev,
                                                               int32_t* __restrict__ tile_start,
                                                               int32_t* __restrict__ tile_count, int32_t* __restrict__ ticket,
                                                               int32_t* __restrict__ status) {
@@ -85,7 +86,15 @@ __global__ void __launch_bounds__(1024) shmp_tile_plan_kernel(const int32_t* __r
   __shared__ int s_cnt;
   const int tid = threadIdx.x;
   const int c0 = blockIdx.x * CH;
+  if (g_dev) G = min(G, *g_dev);  // stream-ordered form: G is a capacity, the batch's own count lives on the device
   const int n = min(CH, G - c0);
+  if (n <= 0) {
+    if (tid == 0) {
+      tile_count[blockIdx.x] = 0;
+      if (blockIdx.x == 0) *ticket = 0;
+    }
+    return;
+  }
   for (int i = tid; i <= n; i += 1024) sP[i] = nbh_ptr[c0 + i];
   if (tid == 0) {
     s_cnt = n;
@@ -137,6 +146,7 @@ __device__ unsigned long long g_phase_cycles[PH_COUNT];
 struct FusedArgs {
   const int32_t* nbh_ptr; const int32_t* edge_ptr; const int32_t* edge_col; const uint8_t* edge_tri;
   const int32_t* tile_start; const int32_t* tile_count; int32_t* ticket;
+  const int32_t* g_dev;     // device-resident neighborhood count (stream-ordered form) or NULL
   int G, num_chunks, pyg_batch_size, layers, passes, input_dim, emb_ld;
   const float* feat;        // [V][input_dim] or NULL (ZeroNodeFeat)
   const float* w_pre;       // per node type (count, canonical): W[input_dim][64], b[64]
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         // SAGEConv.forward runs remove_self_loops on the bipartite count<->canonical relations (gnn_model.py:389-390):
         // see shmp.cu shmp_plan_kernel / DESIGN.md "reference quirks"
         const int g = nb0 + tid;
-        const int bs = p.pyg_batch_size > 0 ? p.pyg_batch_size : p.G;
+        const int bs = p.pyg_batch_size > 0 ? p.pyg_batch_size : (p.g_dev ? *p.g_dev : p.G);
         const int g0 = (g / bs) * bs;
         const int lo = p.nbh_ptr[g];
         sQuirk[tid] = (p.pyg_batch_size >= 0 && lo - p.nbh_ptr[g0] == 2 * (g - g0)) ? (lo - row0) : -1;  // < 0: quirk off
@@ -608,7 +618,7 @@ int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge
                                      const uint8_t* edge_tri, int G, int pyg_batch_size, const float* feat, int input_dim,
                                      const float* w_pre, const void* w_layers_tc, int layers, int passes, float* emb_a,
                                      void* emb_img, float* pool, int emb_ld, void* workspace, int32_t* status,
-                                     cudaStream_t s) {
+                                     const int32_t* g_dev, cudaStream_t s) {
   if (G <= 0) return DESCO_OK;
   if (!status || !workspace || !w_layers_tc) return DESCO_EINVAL;
   const int chunks = (G + CH - 1) / CH;
@@ -617,7 +627,7 @@ int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge
   int32_t* ticket = (int32_t*)((char*)tile_count + ((size_t)chunks * 4 + 255) / 256 * 256);
   {
     DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
-    shmp_tile_plan_kernel<<<chunks, 1024, 0, s>>>(nbh_ptr, G, tile_start, tile_count, ticket, status);
+    shmp_tile_plan_kernel<<<chunks, 1024, 0, s>>>(nbh_ptr, G, g_dev, tile_start, tile_count, ticket, status);
     DESCO_LAUNCH_CHECK();
   }
   static bool attr_set = false;
@@ -627,7 +637,7 @@ int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge
   }
   FusedArgs a;
   a.nbh_ptr = nbh_ptr; a.edge_ptr = edge_ptr; a.edge_col = edge_col; a.edge_tri = edge_tri;
-  a.tile_start = tile_start; a.tile_count = tile_count; a.ticket = ticket;
+  a.tile_start = tile_start; a.tile_count = tile_count; a.ticket = ticket; a.g_dev = g_dev;
   a.G = G; a.num_chunks = chunks; a.pyg_batch_size = pyg_batch_size; a.layers = layers; a.passes = passes;
   a.input_dim = input_dim; a.emb_ld = emb_ld;
   a.feat = feat; a.w_pre = w_pre; a.w_layers = (const uint8_t*)w_layers_tc; a.emb_a = emb_a; a.emb_img = (uint8_t*)emb_img; a.pool = pool; a.status = status;

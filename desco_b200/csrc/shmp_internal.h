@@ -20,24 +20,25 @@ int desco_internal_shmp_fused_layers(const int32_t* nbh_ptr, const int32_t* edge
                                      const uint8_t* edge_tri, int G, int pyg_batch_size, const float* feat, int input_dim,
                                      const float* w_pre, const void* w_layers_tc, int layers, int passes, float* emb_a,
                                      void* emb_img, float* pool, int emb_ld, void* workspace, int32_t* status,
-                                     cudaStream_t s);
+                                     const int32_t* g_dev, cudaStream_t s);
 
 // Y = act(X . W^T + b) (+ R) on tcgen05 (csrc/dense_tc.cu).  Wimg: pack_dense_tc images; act: 0 none, 1 relu, 2 leaky.
 // Ximg != NULL: X comes as ready-made operand images (per block of 128 rows and 64-wide K atom: bf16 hi | mid | lo
 // SWIZZLE_128B images, 3 x 16 KB) and is fetched by bulk async copy instead of being converted by the threads.
+// m_dev / g_dev (may be NULL): device-resident row count of the stream-ordered form; M / G are then capacities.
 int desco_internal_dense_tc(const float* X, const void* Ximg, int ldx, const void* Wimg, const float* bias, const float* R, int ldr, float* Y,
                             int ldy, int M, int K, int N, int nblk, int act, float slope, int passes, int32_t* status,
-                            cudaStream_t s);
+                            const int32_t* m_dev, cudaStream_t s);
 
 // post_mp chain Z[G, K0] -> out[G, 64] in one launch, fp32 (csrc/readout.cu).  Weights row-major [in][out].
 int desco_internal_readout_chain(const float* Z, int ldz, int K0, int G, const float* P0, const float* b0, const float* P1,
                                  const float* b1, const float* P2, const float* b2, const float* P3, const float* b3,
-                                 float* out, cudaStream_t s);
+                                 float* out, const int32_t* g_dev, cudaStream_t s);
 
 // Factorised count head for Q <= 32 queries in one launch, fp32 (csrc/readout.cu); DESCO_ERANGE for larger Q.
 int desco_internal_count_head_fused(const float* emb_t, int G, const float* emb_q, int Q, const float* W1a, const float* W1b,
                                     const float* b1, const float* w2, const float* b2, float* pred, float* count,
-                                    cudaStream_t s);
+                                    const int32_t* g_dev, cudaStream_t s);
 
 /* bytes of one layer in the multi-tile weight blob (csrc/shmp_mt.cu): 3 K blocks x [hi | lo] images of a [64 n x 64 k]
  * block of Wc^T (tcpack.pack_b_operand) */

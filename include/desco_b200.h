@@ -106,6 +106,19 @@ int desco_partition_batch(const int32_t* rowptr, const int32_t* col, const int32
                           int32_t* edge_ptr, int64_t cap_rows, int32_t* edge_col, uint8_t* edge_tri, int64_t cap_edges,
                           int32_t* totals_host, void* stream);
 
+/* Stream-ordered form of desco_partition_batch (no host synchronisation, CUDA-graph capturable): count, scans, a capacity
+ * guard and fill are enqueued back to back; the batch's own sizes stay ON THE DEVICE in sizes_dev (int32[16], caller
+ * allocated): [12..15] = effective {G, V, E, rows of the largest neighborhood} read by the *_dev entry points below,
+ * [0..3] the raw totals, [4] a status word, [8..11] the exact 64-bit row / edge sums.  When the totals exceed cap_rows /
+ * cap_edges nothing is emitted, the effective sizes are 0 and [4] = DESCO_ENOBUFS (DESCO_ERANGE past 2^31): the caller
+ * notices when it next reads sizes_dev and repeats with desco_partition_batch.  Graphs up to 409 600 nodes. */
+int desco_partition_batch_async(const int32_t* rowptr, const int32_t* col, const int32_t* graph_ptr, int32_t num_graphs,
+                                const int32_t* centres, int32_t num_centres, int32_t depth, int32_t mode,
+                                int32_t max_graph_nodes, void* workspace, int64_t workspace_bytes, int32_t* nbh_ptr,
+                                int32_t* centre_out, uint8_t* indicator, int32_t* centre_graph, int32_t* node_gid,
+                                int32_t* edge_ptr, int64_t cap_rows, int32_t* edge_col, uint8_t* edge_tri, int64_t cap_edges,
+                                int32_t* sizes_dev, void* stream);
+
 /* Large-graph variants of passes 1 and 3 (config 5: a 10M-node / 200M-directed-edge target, whose node bitsets no
  * longer fit shared memory; desco_partition_count returns DESCO_ERANGE there).  Same outputs, same reference
  * semantics (data.py:329-396).  An ordinary centre is served by one CTA with a hash set + member list + reached list
@@ -189,6 +202,17 @@ int desco_shmp_forward(const int32_t* nbh_ptr, const int32_t* edge_ptr, const in
                        int32_t hidden, float* out_emb, void* workspace, int64_t workspace_bytes, int32_t precision,
                        int32_t* status, void* stream);
 
+/* Stream-ordered form of desco_shmp_forward for the fused tensor-core path (hetero batches, neighborhoods <= 128 rows):
+ * cap_neighborhoods / cap_rows are CAPACITIES (they size the launch grids and the workspace), the batch's own
+ * {G, V, E, max rows} are read on the device from sizes_dev (int32[4], e.g. desco_partition_batch_async's block + 12).
+ * out_emb rows >= G are not written.  Together with desco_partition_batch_async and desco_count_head_dev the whole
+ * partition -> SHMP -> count-head step is free of host round trips and can be captured in one CUDA graph. */
+int desco_shmp_forward_dev(const int32_t* nbh_ptr, const int32_t* edge_ptr, const int32_t* edge_col, const uint8_t* edge_tri,
+                           int32_t cap_neighborhoods, int32_t cap_rows, const int32_t* sizes_dev, int32_t pyg_batch_size,
+                           const float* feat, int32_t input_dim, const float* w_pre, const void* w_layers_tc,
+                           const float* w_readout, const void* w_readout_tc, int32_t layers, int32_t hidden, float* out_emb,
+                           void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream);
+
 /* The same forward for neighborhoods of ANY size on the tensor cores (csrc/shmp_mt.cu): features stay in HBM between
  * layers, a tile is 128 consecutive count rows whatever neighborhoods they belong to, the edge-type-split gather writes
  * the [128 x 192] operand into shared memory as bf16 hi/lo images and the product runs on tcgen05.  Serves Syn_1827-shaped
@@ -213,6 +237,11 @@ int64_t desco_count_head_workspace_bytes(int32_t num_neighborhoods, int32_t num_
 int desco_count_head(const float* emb_target, int32_t num_neighborhoods, const float* emb_query, int32_t num_queries,
                      const float* w_head, const void* w_head_tc, int32_t hidden, float* out_pred, float* out_count,
                      void* workspace, int64_t workspace_bytes, int32_t precision, int32_t* status, void* stream);
+
+/* Stream-ordered form of desco_count_head (num_queries <= 32): cap_neighborhoods is a capacity, G = sizes_dev[0]. */
+int desco_count_head_dev(const float* emb_target, int32_t cap_neighborhoods, const int32_t* sizes_dev, const float* emb_query,
+                         int32_t num_queries, const float* w_head, int32_t hidden, float* out_pred, float* out_count,
+                         void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Gossip propagation (forward)

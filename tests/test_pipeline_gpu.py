@@ -1,0 +1,78 @@
+"""GPU: the stream-ordered partition -> SHMP -> count-head step (desco_b200.pipeline.NeighborhoodCountStep: no host round
+trip, one CUDA-graph replay per step) against the eager path and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from desco_b200.graph import first_nonempty_centres, gen_enzymes_shaped, gen_mutag_shaped
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(seed=0):
+    from desco_b200.lightning_model import STANDARD_QUERY_IDS, NeighborhoodCountingModel
+    from oracle import model as M
+
+    torch.manual_seed(seed)
+    om = M.NeighborhoodCountingModel().eval()
+    pm = NeighborhoodCountingModel().eval()
+    pm.load_state_dict(om.state_dict())
+    pm = pm.cuda()
+    pm.set_queries(STANDARD_QUERY_IDS)
+    pm.set_pyg_batch_size(512)
+    return om, pm
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_step_equals_eager_path_and_oracle(cuda_device, use_graph):
+    from desco_b200.data import DeviceCSR, partition_batch
+    from desco_b200.pipeline import NeighborhoodCountStep
+    from oracle import model as M
+    from oracle import partition as P
+
+    om, pm = _model(2)
+    csr = gen_enzymes_shaped(seed=5, num_graphs=60)
+    g = DeviceCSR.from_host(csr)
+    all_c = np.arange(csr.num_nodes)
+    c1, c2 = all_c[:1000], all_c[700:1700]  # the second batch holds edge-free (dropped) neighborhoods as well
+    step = NeighborhoodCountStep(pm, g, torch.as_tensor(c1, dtype=torch.int32), depth=4, use_cuda_graph=use_graph)
+    for centres in (c1, c2, c1):
+        ct = torch.as_tensor(centres, dtype=torch.int32, device="cuda")
+        step(ct)
+        counts, kept = step.result()
+        with torch.no_grad():
+            eager_b = partition_batch(g, ct, 4, "hetero")
+            eager = pm.graph_to_count(eager_b)
+        assert torch.equal(kept, eager_b.centre) and torch.equal(counts, eager)
+        assert torch.equal(step.nbh_ptr[: eager_b.num_neighborhoods + 1], eager_b.nbh_ptr)
+        assert torch.equal(step.edge_tri[: eager_b.num_edges], eager_b.edge_tri)
+    ref = P.partition_dataset(csr, 4, centres=c1)
+    with torch.no_grad():
+        want = om.graph_to_count(ref, M.query_batch(), pyg_batch_size=512)
+    assert ((counts.cpu() - want).abs() / want.abs().clamp(min=1.0)).max().item() <= 1e-4
+
+
+def test_step_reports_capacity_overflow_and_unsupported_batches(cuda_device):
+    from desco_b200 import _lib
+    from desco_b200.data import DeviceCSR
+    from desco_b200.graph import gen_syn1827_shaped
+    from desco_b200.pipeline import NeighborhoodCountStep
+
+    _, pm = _model(3)
+    csr = gen_enzymes_shaped(seed=6, num_graphs=80)
+    g = DeviceCSR.from_host(csr)
+    sizes = np.diff(csr.graph_ptr)
+    small_first = np.concatenate([np.arange(csr.graph_ptr[i], csr.graph_ptr[i + 1]) for i in np.argsort(sizes)])
+    n = 400
+    step = NeighborhoodCountStep(pm, g, torch.as_tensor(small_first[:n], dtype=torch.int32), depth=4, margin=1.0)
+    step(torch.as_tensor(small_first[-n:], dtype=torch.int32))  # the largest graphs: far more rows than the capacity
+    with pytest.raises(_lib.DescoError):
+        step.result()
+    step(torch.as_tensor(small_first[:n], dtype=torch.int32))  # and the step is usable again afterwards
+    counts, kept = step.result()
+    assert counts.shape[0] == kept.shape[0] > 0 and torch.isfinite(counts).all()
+    big = DeviceCSR.from_host(gen_syn1827_shaped(seed=1, stride=300))  # neighborhoods beyond one 128-row tile
+    with pytest.raises(NotImplementedError):
+        NeighborhoodCountStep(pm, big, torch.arange(big.num_nodes, dtype=torch.int32), depth=4)
+    with pytest.raises(ValueError):
+        step(torch.zeros(7, dtype=torch.int32))
