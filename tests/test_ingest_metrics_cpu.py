@@ -56,3 +56,28 @@ def test_metrics_match_their_definitions():
     assert mae(pred, truth, groups) == pytest.approx([np.mean(np.abs(pred[:, g] - truth[:, g])) for g in groups])
     assert norm_mse(truth, truth, groups) == [0.0, 0.0]
     assert round_counts(np.array([-0.4, 0.49, 2.5, 3.51])).tolist() == [0.0, 0.0, 2.0, 4.0]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted")
+def test_metrics_equal_the_reference_functions_executed_from_source():
+    """norm_mse / mse / mae of subgraph_counting/analysis.py:22-83 (pure numpy; the module itself imports the whole package)
+    compiled from the reference source and run on the same arrays."""
+    import ast
+
+    path = "/root/reference/subgraph_counting/analysis.py"
+    tree = ast.parse(open(path).read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("norm_mse", "mse", "mae")]
+    for fn in body:
+        fn.returns = None
+        for a in fn.args.args:
+            a.annotation = None
+    ns = {"np": np}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    rng = np.random.default_rng(1)
+    truth = np.floor(np.exp(rng.normal(0, 1.5, size=(80, 29)))).astype(np.float32)
+    pred = (truth + rng.normal(0, 1.0, size=truth.shape)).astype(np.float32)
+    groups = [[0, 1], list(range(2, 8)), list(range(8, 29))]  # the paper's 3- / 4- / 5-node query groups
+    for ours, name in ((norm_mse, "norm_mse"), (mse, "mse"), (mae, "mae")):
+        assert ours(pred, truth, groups) == pytest.approx(ns[name](pred, truth, groups), rel=1e-12)
+    assert norm_mse(pred, truth) == pytest.approx(ns["norm_mse"](pred, truth), rel=1e-12)
+    assert mse(pred, truth) == pytest.approx(ns["mse"](pred, truth), rel=1e-12)
