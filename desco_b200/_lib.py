@@ -119,6 +119,11 @@ SIGNATURES = {
     "desco_gossip_layer1_group": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _I, _I, _VP, _L, _VP]),
     "desco_gossip_layer1_workspace_bytes": (_L, [_I, _I, _I]),
     "desco_groundtruth_count": (_I, [_VP, _VP, _VP, _I, _I, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP]),
+    "desco_gossip_gated_mix": (_I, [_VP, _VP, _VP, _VP, _L, _VP]),
+    "desco_gossip_gate_grad": (_I, [_VP, _VP, _VP, _L, _VP, _VP]),
+    "desco_gossip_gate_backward": (_I, [_VP, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "desco_train_dropout": (_I, [_VP, _VP, _F, _L, _VP]),
+    "desco_gossip_loss": (_I, [_VP, _I, _VP, _I, _VP, _I, _I, _VP, _VP, _I, _VP, _VP]),
     "desco_spmm_sum": (_I, [_VP, _VP, _VP, _I, _VP, _I, _I, _VP, _I, _VP]),
     "desco_gossip_gate": (_I, [_VP, _I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP]),
     "desco_shmp_fused_phase_cycles": (_I, [_VP, _I]),

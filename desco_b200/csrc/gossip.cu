@@ -113,10 +113,18 @@ __global__ void gossip_layer0_kernel(const int32_t* __restrict__ rowptr, const i
     const int q = q0 + lane;
     float s_lt = 0.f, s_gt = 0.f;
     int d_lt = 0;
-    for (int e = eb; e < ee; ++e) {
-      const int j = col[e];
-      const float c = (q < Q) ? x[(size_t)j * Q + q] : 0.f;
-      if (j < i) { s_lt += c; ++d_lt; } else { s_gt += c; }
+    // 32 adjacency entries per step (one coalesced load), then the 32 neighbours' count rows back to back: the loads are
+    // independent, so a hub row (10^4 neighbours, one warp) keeps eight 116-byte row reads in flight instead of one
+    for (int base = eb; base < ee; base += 32) {
+      const int myj = (base + lane < ee) ? col[base + lane] : 0x7fffffff;
+      const int n = min(32, ee - base);
+      d_lt += __popc(__ballot_sync(FULL_MASK, myj < i));
+#pragma unroll 8
+      for (int k = 0; k < n; ++k) {
+        const int j = __shfl_sync(FULL_MASK, myj, k);
+        const float c = (q < Q) ? __ldg(x + (size_t)j * Q + q) : 0.f;
+        if (j < i) s_lt += c; else s_gt += c;
+      }
     }
     if (q < Q) {
       const float g0 = qvec[(size_t)q * QV + 3 * F], g1 = qvec[(size_t)q * QV + 3 * F + 1];

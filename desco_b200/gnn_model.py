@@ -485,8 +485,9 @@ class GossipBaseGNN(_PackedWeightsMixin, nn.Module):
 
     def forward_all_queries(self, rowptr, col, x, query_emb, want_gates=False):
         """out[N,Q] = x + gossip correction for every query column at once."""
-        if self.training:
-            raise NotImplementedError("gossip training (dropout 0.01 + backward) is not a CUDA path yet")
+        if self.training and self.gnn_core.dropout > 0:
+            raise NotImplementedError("the fused gossip forward is the inference path (eval mode, lightning_model.py:613-628); "
+                                      "training goes through GossipCountingModel.train_forward (desco_b200/gossip_training.py)")
         lib = _lib.load()
         w = self.packed_weights()
         dev = w["wg"].device
@@ -522,8 +523,8 @@ class GossipShardedRun:
     def __init__(self, model: "GossipBaseGNN", rowptr, col, x, query_emb, comm, query_group: int = 4, gather_output: bool = True):
         from .distributed import gossip_shard_plan
 
-        if model.training:
-            raise NotImplementedError("gossip training is not a CUDA path yet")
+        if model.training and model.gnn_core.dropout > 0:
+            raise NotImplementedError("the sharded gossip forward is the inference path; see gossip_training.py for training")
         self.m, self.rowptr, self.col, self.comm, self.gather_output = model, rowptr, col, comm, gather_output
         self.lib = _lib.load()
         self.w = model.packed_weights()

@@ -263,6 +263,11 @@ class GossipCountingModel(nn.Module):
         self.query_emb = None
         self.eval()
 
+    def train(self, mode: bool = True):
+        out = super().train(mode)
+        self.emb_model._invalidate_caches()
+        return out
+
     load_from_checkpoint = classmethod(_load_lightning_checkpoint)
 
     def set_query_emb(self, query_emb: torch.Tensor, query_ids=None, queries=None):
@@ -281,6 +286,32 @@ class GossipCountingModel(nn.Module):
 
     def forward(self, batch):
         return self.graph_to_count(batch)
+
+    # ---- training (csrc/gossip_train.cu through desco_b200/gossip_training.py) ----
+    def train_forward(self, batch, batch_idx=0) -> torch.Tensor:
+        """``lightning_model.py:585-608``: sum over queries and nodes of ``log2(|x + gossip(x) - y| + 1)``; the returned
+        scalar carries a grad_fn over the gossip parameters (``pre_mp`` / ``anchor_mlp`` get none, as in the reference)."""
+        from .gossip_training import gossip_train_forward
+
+        return gossip_train_forward(self, batch)
+
+    def training_step(self, batch, batch_idx=0) -> torch.Tensor:  # :553-556
+        return self.train_forward(batch, batch_idx)
+
+    def validation_step(self, batch, batch_idx=0) -> torch.Tensor:  # :562-564
+        return self.train_forward(batch, batch_idx).detach()
+
+    def test_step(self, batch, batch_idx=0) -> torch.Tensor:  # :558-560
+        return self.train_forward(batch, batch_idx).detach()
+
+    def criterion(self, count: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:  # :630-635
+        return torch.log2(torch.abs(count - truth) + 1)
+
+    def configure_optimizers(self):
+        """``lightning_model.py:570-583``: Adam(lr, weight_decay) + ReduceLROnPlateau(min, 0.5, patience 20, 1e-5)."""
+        opt = torch.optim.Adam(self.parameters(), lr=getattr(self, "lr", 1e-3), weight_decay=getattr(self, "weight_decay", 0.0))
+        sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.5, patience=20, min_lr=1e-5)
+        return {"optimizer": opt, "lr_scheduler": sched, "monitor": "gossip_counting_val_loss"}
 
     def _gate_value(self, query_emb) -> torch.Tensor:
         """``lightning_model.py:640-649``: (#layers, #queries, 1)."""

@@ -327,6 +327,27 @@ int desco_gossip_gate(const float* query_emb, int32_t num_queries, int32_t emb_c
                       int32_t hidden, const float* w2, const float* b2, float* gate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Training step of the gossip model (csrc/gossip_train.cu)
+ * Replaces: GossipCountingModel.train_forward / criterion (lightning_model.py:585-608, 630-635) and autograd through
+ *           GossipConv (gnn_model.py:294-348).  The matrix work runs on desco_train_dense / desco_train_wgrad /
+ *           desco_spmm_sum (whose adjoint on a symmetric edge set is the same call with the two gate weights swapped);
+ *           these are the remaining pieces, all stream-ordered with the gate as a DEVICE scalar:
+ *   gated_mix      out = g a + (1 - g) b                              (the two directional aggregates -> the message sum)
+ *   gate_grad      *dgate += <d, a - b>                               (d loss / d gate)
+ *   gate_backward  gradients of lin_gate (Linear, Sigmoid, Linear, Sigmoid, LeakyReLU) from *dgate, accumulated (+=)
+ *   train_dropout  x *= mask ? scale : 0                              (F.dropout / nn.Dropout in training mode)
+ *   gossip_loss    pred = c + out;  *loss += sum log2(|pred - y| + 1);  dout = d loss / d out   (strided columns)
+ * ---------------------------------------------------------------------------------------------------------------- */
+int desco_gossip_gated_mix(const float* a, const float* b, const float* gate, float* out, int64_t n, void* stream);
+int desco_gossip_gate_grad(const float* d, const float* a, const float* b, int64_t n, float* dgate, void* stream);
+int desco_gossip_gate_backward(const float* query_emb, int32_t emb_channels, const float* w1, const float* b1, int32_t hidden,
+                               const float* w2, const float* b2, const float* dgate, float* dw1, float* db1, float* dw2,
+                               float* db2, void* stream);
+int desco_train_dropout(float* x, const uint8_t* mask, float scale, int64_t n, void* stream);
+int desco_gossip_loss(const float* c, int32_t ldc, const float* out, int32_t ldo, const float* y, int32_t ldy, int32_t n,
+                      float* pred, float* dout, int32_t ldd, float* loss, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Training step of the neighborhood-counting model (BASELINE config 3)
  * Replaces: NeighborhoodCountingModel.train_forward (lightning_model.py:228-254), criterion (:285-289),
  *           configure_optimizers / torch.optim.Adam (:160-173) and the autograd graph through gnn_model.py:58-109,

@@ -331,6 +331,16 @@ class GossipCountingModel(nn.Module):
             out.append(c + self.emb_model(c, edge_index, self.query_emb[q].view(1, -1)))
         return torch.cat(out, dim=-1)
 
+    def train_forward(self, x: torch.Tensor, y: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+        """``lightning_model.py:585-608`` with ``criterion`` :630-635: sum over queries and nodes of
+        ``log2(|x_q + gossip(x_q) - y_q| + 1)``."""
+        losses = []
+        for q in range(x.shape[1]):
+            c = x[:, q].view(-1, 1)
+            pred = c + self.emb_model(c, edge_index, self.query_emb[q].view(1, -1))
+            losses.append(torch.log2(torch.abs(pred - y[:, q].view(-1, 1)) + 1))
+        return torch.sum(torch.stack(losses))
+
     def gate_value(self, query_emb):
         return torch.stack([c.lin_gate(query_emb) for c in self.emb_model.gnn_core.convs], dim=0)  # :640-649
 
