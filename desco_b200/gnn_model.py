@@ -409,6 +409,7 @@ class GossipCore(nn.Module):
         if args.conv_type != "GOSSIP" or args.layer_num != 2 or hidden_dim != 64 or emb_channels != 64 or input_dim != 1:
             raise NotImplementedError("the gossip kernels are specialised for config.py:312-322 defaults "
                                       "(GOSSIP, 2 layers, hidden 64, query embedding 64, input_dim 1)")
+        self.dropout = float(args.dropout)  # F.dropout after every conv in training mode (gnn_model.py:274; config.py:316: 0.01)
         self.pre_mp = nn.Sequential(nn.Linear(input_dim, hidden_dim))
         self.convs = nn.ModuleList()
         for l in range(args.layer_num):
