@@ -269,6 +269,21 @@ __global__ void shmp_pool_last_kernel(const int32_t* __restrict__ nbh_ptr, int G
   *reinterpret_cast<float2*>(pool + (size_t)g * emb_ld + layer * F + 2 * lane) = ps;
 }
 
+// Homogeneous model (hetero_graph = False, gnn_model.py:74-83): the centre is an ordinary row of its neighborhood (the last
+// one) whose skip-concat embedding goes through anchor_mlp before the pooling.  Its per-layer rows are collected here ...
+__global__ void shmp_copy_last_rows_kernel(const int32_t* __restrict__ nbh_ptr, int G, const float* __restrict__ h, int layer,
+                                           float* __restrict__ emb_a, int emb_ld) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= G) return;
+  const size_t row = (size_t)nbh_ptr[g + 1] - 1;
+  reinterpret_cast<float2*>(emb_a + (size_t)g * emb_ld + layer * F)[lane_id()] = reinterpret_cast<const float2*>(h + row * F)[lane_id()];
+}
+// ... and taken out of the all-rows pool again: z = (pool - emb_centre) + anchor_mlp(emb_centre)
+__global__ void shmp_sub_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] -= b[i];
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // dense row-wise layer for the readout MLPs:  Y = act(X . W + b) (+ R)
 // ------------------------------------------------------------------------------------------------------------------
@@ -416,6 +431,11 @@ Workspace carve(void* base, int V, int G, int layers) {
 void desco_internal_shmp_cvec(const float* emb_a, int emb_ld, int layer, const float* Cw, int G, float* cvec, cudaStream_t s) {
   shmp_cvec_kernel<<<(G + 7) / 8, 256, 0, s>>>(emb_a, emb_ld, layer, Cw, G, cvec);
 }
+void desco_internal_shmp_copy_last_rows(const int32_t* nbh_ptr, int G, const float* h, int layer, float* emb_a, int emb_ld,
+                                        cudaStream_t s) {
+  desco_count_launches(1);
+  shmp_copy_last_rows_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, G, h, layer, emb_a, emb_ld);
+}
 
 extern "C" {
 
@@ -437,14 +457,18 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
   // sizes_dev != NULL: the stream-ordered form - num_neighborhoods / num_rows are CAPACITIES and the batch's own
   // {G, V, E, max rows} are read on the device (fused tensor-core path only)
   const int G = num_neighborhoods, V = num_rows;
-  if (hidden != F || layers < 1 || input_dim < 1 || G < 0 || V < 0) return DESCO_EINVAL;
+  if (hidden != F || layers < 1 || input_dim < 1 || G < 0 || V < 0 || hetero < 0 || hetero > 2) return DESCO_EINVAL;
   if (precision < DESCO_PRECISION_FP32 || precision > DESCO_PRECISION_BF16) return DESCO_EINVAL;
   if (G == 0) return DESCO_OK;
   if (!nbh_ptr || !edge_ptr || !edge_col || !edge_tri || !w_pre || !w_readout || !out_emb || !workspace) return DESCO_EINVAL;
+  // hetero = 2: one node type, but the LAST row of every neighborhood (the centre, marked by node_feature = 1) goes through
+  // anchor_mlp before the pooling - the homogeneous model of hetero_graph = False (gnn_model.py:74-83, workload.py:238-241)
+  const bool anchored = hetero == 2;
+  if (anchored) hetero = 0;
   const bool mt = w_layers_mt != nullptr && precision != DESCO_PRECISION_FP32;  // multi-tile tcgen05 path (any size)
   const bool fused = !mt && precision != DESCO_PRECISION_FP32;
   if (fused && (!hetero || !w_layers_tc || !w_readout_tc || !status)) return DESCO_EINVAL;  // tensor-core path: count/canonical batches
-  if (mt && (!w_layers || !status || (hetero && !w_readout_tc))) return DESCO_EINVAL;
+  if (mt && (!w_layers || !status || ((hetero || anchored) && !w_readout_tc))) return DESCO_EINVAL;
   if (sizes_dev && !fused) return DESCO_EINVAL;
   if (!fused && !w_layers) return DESCO_EINVAL;
   Workspace ws = carve(workspace, V, G, layers);
@@ -477,7 +501,7 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
     const int rc = desco_internal_shmp_mt_layers(nbh_ptr, edge_ptr, edge_col, edge_tri, G, V, hetero, ws.row_nbh, ws.crow,
                                                  ws.canon_code, ws.quirk_row, ws.hA, ws.hB, ws.emb_a, ws.pool, ws.cvec, emb_ld,
                                                  w_layers, desco_shmp_layer_weight_floats(), w_layers_mt, layers,
-                                                 precision == DESCO_PRECISION_BF16X3 ? 3 : 1, ws.mt, status, s);
+                                                 precision == DESCO_PRECISION_BF16X3 ? 3 : 1, ws.mt, status, anchored ? 1 : 0, s);
     if (rc) return rc;
   } else {
   const size_t smem = (size_t)(TM * LDA + KC * F) * sizeof(float) + 3 * TM * sizeof(int);
@@ -504,6 +528,7 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
       shmp_cvec_kernel<<<(G + 7) / 8, 256, 0, s>>>(ws.emb_a, emb_ld, l, wl + KC * F + F, G, ws.cvec);
       DESCO_LAUNCH_CHECK();
     }
+    if (anchored) desco_internal_shmp_copy_last_rows(nbh_ptr, G, h_in, l, ws.emb_a, emb_ld, s);
     {
       DescoProfScope prof(DESCO_PROF_SHMP_LAYER, s);
       shmp_layer_kernel<<<grid, THREADS, smem, s>>>(a);
@@ -516,8 +541,15 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
     shmp_pool_last_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, G, hetero, h_in, layers, ws.pool, emb_ld);
     DESCO_LAUNCH_CHECK();
   }
+  if (anchored) desco_internal_shmp_copy_last_rows(nbh_ptr, G, h_in, layers, ws.emb_a, emb_ld, s);
   }  // layer-by-layer FFMA kernels
   }  // layered paths
+  if (anchored) {  // the pool above covers every row: take the centre rows out, anchor_mlp puts them back below
+    const long long n = (long long)G * emb_ld;
+    desco_count_launches(1);
+    shmp_sub_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ws.pool, ws.emb_a, n);
+    DESCO_LAUNCH_CHECK();
+  }
 
   // readout: [Wanc (emb_ld x emb_ld) | banc | P0 (emb_ld x F) | b0 | P1 (F x F) | b1 | P2 (F x 4F) | b2 | P3 (4F x F) | b3]
   const float* r = w_readout;
@@ -533,7 +565,7 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
   const float* b3 = r;
   int rc;
   const float* z = ws.pool;
-  if (fused || (mt && hetero)) {  // the same chain on the tensor pipe (csrc/dense_tc.cu); images in w_readout_tc, biases from w_readout
+  if (fused || (mt && (hetero || anchored))) {  // the same chain on the tensor pipe (csrc/dense_tc.cu); images in w_readout_tc, biases from w_readout
     const int passes = precision == DESCO_PRECISION_BF16X3 ? 6 : 1;  // the readout sums cancel heavily: full 3-way split
     // bf16 hi + mid + lo = 6 bytes per weight; the blob starts with the anchor_mlp images (the post_mp images that follow
     // are for a dense_tc post_mp chain; the default chain below is the single-launch fp32 kernel)
@@ -546,7 +578,7 @@ static int shmp_forward_impl(const int32_t* nbh_ptr, const int32_t* edge_ptr, co
                                       G, emb_ld, emb_ld, 144, 2, 0.1f, passes, status, sizes_dev, s))) return rc;
     return desco_internal_readout_chain(ws.z, emb_ld, emb_ld, G, P0, b0, P1, b1, P2, b2, P3, b3, out_emb, sizes_dev, s);
   }
-  if (hetero) {  // z = pool_count + LeakyReLU_0.1(anchor(emb_canonical))  (gnn_model.py:69-73, 88-89, 107)
+  if (hetero || anchored) {  // z = pool_count + LeakyReLU_0.1(anchor(emb_canonical))  (gnn_model.py:69-73, 88-89, 107)
     rc = dense(ws.emb_a, emb_ld, Wanc, banc, ws.pool, emb_ld, ws.z, emb_ld, G, emb_ld, emb_ld, ACT_LEAKY, 0.1f, s);
     if (rc) return rc;
     z = ws.z;

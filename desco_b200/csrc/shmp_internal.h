@@ -50,6 +50,9 @@ int desco_internal_shmp_mt_layers(const int32_t* nbh_ptr, const int32_t* edge_pt
                                   const int32_t* crow, const uint8_t* canon_code, const int32_t* quirk_row, float* hA,
                                   float* hB, float* emb_a, float* pool, float* cvec, int emb_ld, const float* w_layers,
                                   int64_t layer_floats, const void* w_layers_mt, int layers, int passes, void* workspace,
-                                  int32_t* status, cudaStream_t s);
+                                  int32_t* status, int anchored, cudaStream_t s);
+// emb_a[g][layer*64 ..] = h[last row of neighborhood g]  (shmp.cu; the homogeneous model's centre rows)
+void desco_internal_shmp_copy_last_rows(const int32_t* nbh_ptr, int G, const float* h, int layer, float* emb_a, int emb_ld,
+                                        cudaStream_t s);
 // cvec[g] = h_canonical^l[g] . Cw^l (shmp.cu)
 void desco_internal_shmp_cvec(const float* emb_a, int emb_ld, int layer, const float* Cw, int G, float* cvec, cudaStream_t s);

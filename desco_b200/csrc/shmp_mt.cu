@@ -420,7 +420,7 @@ int desco_internal_shmp_mt_layers(const int32_t* nbh_ptr, const int32_t* edge_pt
                                   const int32_t* crow, const uint8_t* canon_code, const int32_t* quirk_row, float* hA,
                                   float* hB, float* emb_a, float* pool, float* cvec, int emb_ld, const float* w_layers,
                                   int64_t layer_floats, const void* w_layers_mt, int layers, int passes, void* workspace,
-                                  int32_t* status, cudaStream_t s) {
+                                  int32_t* status, int anchored, cudaStream_t s) {
   const int Vc = hetero ? V - G : V;
   const int KC = 3 * F;
   float* partial = (float*)workspace;
@@ -439,6 +439,7 @@ int desco_internal_shmp_mt_layers(const int32_t* nbh_ptr, const int32_t* edge_pt
     const long long warps = ((long long)V + PSUB - 1) / PSUB;
     shmp_mt_pool_partial_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(row_nbh, h, V, partial);
     shmp_mt_pool_reduce_kernel<<<(G * 32 + 255) / 256, 256, 0, s>>>(nbh_ptr, G, partial, pool, emb_ld, l);
+    if (anchored) desco_internal_shmp_copy_last_rows(nbh_ptr, G, h, l, emb_a, emb_ld, s);  // homogeneous model: centre rows
     DESCO_LAUNCH_CHECK();
     return DESCO_OK;
   };

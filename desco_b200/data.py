@@ -258,6 +258,8 @@ def partition_batch(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: in
         graph.graph_ptr, G, V, E, hetero=(mode == MODE_HETERO),
         max_rows=max_nv,  # rows of the largest neighborhood (selects the fused SHMP kernel)
     )
+    if mode == MODE_CANONICAL:
+        batch._cache["centre_last"] = True  # get_neigh_canonical marks the centre (last row) with node_feature = 1
     if large:
         batch._cache["tier"] = lwork[:C].clone()  # which tier served each centre (0 shared-memory hash, 1 team bitmap)
     return batch
@@ -327,10 +329,13 @@ def _partition_batch_one_call(lib, graph: DeviceCSR, centres: torch.Tensor, C: i
     if C and V:
         _CAPACITY["rows_per_centre"] = max(_CAPACITY["rows_per_centre"], V / C)
         _CAPACITY["edges_per_row"] = max(_CAPACITY["edges_per_row"], E / V)
-    return NeighborhoodBatch(
+    batch = NeighborhoodBatch(
         nbh_ptr[: G + 1], rows[0, :V], rows[1, : V + 1], edge_col[:E], edge_tri[:E], centre_out[:G], indicator[:C], cg[:C],
         graph.graph_ptr, G, V, E, hetero=(mode == MODE_HETERO), max_rows=max_nv,
     )
+    if mode == MODE_CANONICAL:
+        batch._cache["centre_last"] = True  # get_neigh_canonical marks the centre (last row) with node_feature = 1
+    return batch
 
 
 def shmp_edge_types(edge_ptr: torch.Tensor, edge_col: torch.Tensor) -> torch.Tensor:

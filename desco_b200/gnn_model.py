@@ -35,6 +35,8 @@ QUERY_META = (
     [("union_node", "union_triangle", "union_node"), ("union_node", "union_tride", "union_node")],
 )  # lightning_model.py:404-413
 
+HOMOG_META = (["node"], [("node", "union", "node")])  # hetero_graph = False: one node type, one relation (ablation_gnns.py)
+
 PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 TILE_ROWS = 128  # csrc/shmp_internal.h SHMP_TILE_ROWS
 
@@ -197,17 +199,38 @@ class BaseGNNCore(nn.Module):
         self.post_input_dim = hidden_dim * args.layer_num + hidden_dim
 
 
+class HomogGNNCore(nn.Module):
+    """``BaseGNNCore`` (``gnn_model.py:115-277``) as the reference builds it BEFORE ``to_hetero``: the homogeneous SAGE model
+    of ``hetero_graph=False`` (``workload.py:238-241``, ``ablation_gnns.py``) - one node type, one relation, the centre marked
+    by ``node_feature = 1``.  State-dict keys are the reference's own (``pre_mp.0``, ``convs.<l>.lin``, ``updates.<l>``)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, args, **kwargs):
+        super().__init__()
+        if args.conv_type != "SAGE" or hidden_dim != 64:
+            raise NotImplementedError("the sm_100a kernels serve the default SAGE core with hidden_dim = 64")
+        self.meta = HOMOG_META
+        self.layer_num, self.input_dim, self.hidden_dim, self.dropout = args.layer_num, input_dim, hidden_dim, args.dropout
+        self.pre_mp = nn.Sequential(nn.Linear(input_dim, hidden_dim))
+        self.convs = nn.ModuleList()
+        self.updates = nn.ModuleList()
+        for _ in range(args.layer_num):  # gnn_model.py:146-190: conv then update, layer by layer
+            self.convs.append(SAGEConv(hidden_dim, hidden_dim))
+            self.updates.append(nn.Linear(2 * hidden_dim, hidden_dim))
+        self.post_input_dim = hidden_dim * args.layer_num + hidden_dim
+
+
 def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
     """Fuse + transpose the parameters into the blobs of include/desco_b200.h (fp64 on the host, rounded once)."""
     core = base.gnn_core
     hetero = "canonical" in core.meta[0]
+    homog = isinstance(core, HomogGNNCore)
     types = core.meta[0]
     F = core.hidden_dim
     dev = base.post_mp[0].weight.device
     d = lambda t: t.detach().to("cpu", torch.float64)
     pre = []
     for t in types:
-        lin = core.pre_mp[0][t]
+        lin = core.pre_mp[0] if homog else core.pre_mp[0][t]
         pre += [d(lin.weight).t().contiguous().flatten(), d(lin.bias)]
     layers = []
     tc_layers = []
@@ -231,6 +254,15 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
             blocks_a, Uma, Uha, ua = fused("canonical", ca)
             Wa = torch.cat(blocks_a + [Uha.t()], 0)
             bias_a = Uma @ sum(d(core.convs[l][_key(r)].lin.bias) for r in ca) + ua
+        elif homog:  # one relation: the triangle and the tride slots of the single-type kernels carry the SAME weights
+            U, u = d(core.updates[l].weight), d(core.updates[l].bias)
+            Um, Uh = U[:, :F], U[:, F:]
+            blk = (Um @ d(core.convs[l].lin.weight)).t()
+            Wc = torch.cat([blk, blk, Uh.t()], 0)
+            bias_c = Um @ d(core.convs[l].lin.bias) + u
+            Cw = torch.zeros(F, 2 * F, dtype=torch.float64)
+            Wa = torch.zeros(3 * F, F, dtype=torch.float64)
+            bias_a = torch.zeros(F, dtype=torch.float64)
         else:
             uu = [("union_node", "union_triangle", "union_node"), ("union_node", "union_tride", "union_node")]
             blocks, Um, Uh, u = fused("union_node", uu)
@@ -252,10 +284,11 @@ def pack_shmp_weights(base: "BaseGNN") -> Dict[str, torch.Tensor]:
     f32 = lambda parts: torch.cat(parts).to(torch.float32).to(dev).contiguous()
     out = {"pre": f32(pre), "layers": f32(layers), "readout": f32(ro), "layers_mt": torch.cat(mt_layers).to(dev).contiguous()}
     assert out["layers_mt"].numel() == core.layer_num * _lib.load().desco_shmp_mt_layer_bytes()
-    if tc_layers:
+    if tc_layers or homog:
         out["readout_tc"] = torch.cat([pack_dense_tc(d(base.anchor_mlp[0].weight), 144), pack_dense_tc(d(base.post_mp[0].weight), 64),
                                        pack_dense_tc(d(base.post_mp[3].weight), 64), pack_dense_tc(d(base.post_mp[5].weight), 128),
                                        pack_dense_tc(d(base.post_mp[7].weight), 64)]).to(dev).contiguous()
+    if tc_layers:
         out["layers_tc"] = torch.cat(tc_layers).to(dev).contiguous()
         assert out["layers_tc"].numel() == core.layer_num * _lib.load().desco_shmp_tc_layer_bytes()
     return out
@@ -271,7 +304,10 @@ class BaseGNN(_PackedWeightsMixin, nn.Module):
         self.args, self.kwargs = args, kwargs
         self.dropout, self.layer_num, self.conv_type = args.dropout, args.layer_num, args.conv_type
         self.use_hetero = getattr(args, "use_hetero", True)
-        self.gnn_core = BaseGNNCore(input_dim, hidden_dim, output_dim, args, meta, **kwargs)
+        if meta is HOMOG_META or not self.use_hetero:
+            self.gnn_core = HomogGNNCore(input_dim, hidden_dim, output_dim, args, **kwargs)
+        else:
+            self.gnn_core = BaseGNNCore(input_dim, hidden_dim, output_dim, args, meta, **kwargs)
         p = self.gnn_core.post_input_dim
         self.anchor_mlp = nn.Sequential(nn.Linear(p, p), nn.LeakyReLU(0.1))
         self.post_mp = nn.Sequential(
@@ -296,8 +332,15 @@ class BaseGNN(_PackedWeightsMixin, nn.Module):
         lib = _lib.load()
         core = self.gnn_core
         hetero = "canonical" in core.meta[0]
+        homog = isinstance(core, HomogGNNCore)
         if hetero != data.hetero:
             raise ValueError("batch node-type layout does not match the model metadata (count/canonical vs union_node)")
+        # homogeneous model: canonical-mode neighborhoods carry their centre as the LAST row, marked by node_feature = 1
+        # (data.py:369-371) - that row goes through anchor_mlp (gnn_model.py:74-83); query graphs have no marked node
+        anchored = homog and bool(data._cache.get("centre_last"))
+        if anchored and feat is None:
+            feat = torch.zeros((data.num_rows, core.input_dim), dtype=torch.float32, device=data.nbh_ptr.device)
+            feat[(data.nbh_ptr[1:] - 1).long(), 0] = 1.0
         if self.training and core.dropout > 0:
             raise NotImplementedError("dropout > 0 in training mode is not a CUDA path (config.py:252 default is 0)")
         w = self.packed_weights()
@@ -315,15 +358,15 @@ class BaseGNN(_PackedWeightsMixin, nn.Module):
         # leave the chip); anything larger takes the multi-tile kernels (features in HBM between layers, any size);
         # query graphs (single node type, a few dozen rows, embeddings cached) stay on the fp32 kernels
         precision = PRECISION[self.precision]
-        if not hetero and not self.force_multi_tile:
+        if not hetero and not anchored and not self.force_multi_tile:
             precision = 0
         multi_tile = precision != 0 and (self.force_multi_tile or not hetero or data.max_rows > TILE_ROWS)
         status = torch.zeros(1, dtype=torch.int32, device=dev) if precision else None
         with torch.cuda.device(dev):
             # PyG-shaped input IS one collated batch: the remove_self_loops quirk is evaluated over it as a whole
             pyg_bs = int(self.pyg_batch_size) if not data._cache.get("pyg_collated") else min(int(self.pyg_batch_size), 0)
-            common = (_ptr(data.nbh_ptr), _ptr(data.edge_ptr), _ptr(data.edge_col), _ptr(data.edge_tri), G, V, int(hetero),
-                      pyg_bs, _ptr(feat), core.input_dim, _ptr(w["pre"]), _ptr(w["layers"]))
+            common = (_ptr(data.nbh_ptr), _ptr(data.edge_ptr), _ptr(data.edge_col), _ptr(data.edge_tri), G, V,
+                      2 if anchored else int(hetero), pyg_bs, _ptr(feat), core.input_dim, _ptr(w["pre"]), _ptr(w["layers"]))
             tail = (_ptr(w["readout"]), _ptr(w.get("readout_tc")), core.layer_num, core.hidden_dim, _ptr(out), _ptr(work),
                     wbytes, precision, _ptr(status), _stream())
             if multi_tile:

@@ -113,8 +113,14 @@ class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
             if not hasattr(self, k):
                 setattr(self, k, v)
         self.query_loader = None  # the reference holds a DataLoader of query graphs; here: one packed batch
-        self.emb_model = BaseGNN(input_dim, hidden_dim, hidden_dim, args, TARGET_META, emb_channels=hidden_dim, **kwargs)
-        self.emb_model_query = BaseGNN(input_dim, hidden_dim, hidden_dim, args, QUERY_META, emb_channels=hidden_dim, **kwargs)
+        if getattr(args, "use_hetero", True):
+            self.emb_model = BaseGNN(input_dim, hidden_dim, hidden_dim, args, TARGET_META, emb_channels=hidden_dim, **kwargs)
+            self.emb_model_query = BaseGNN(input_dim, hidden_dim, hidden_dim, args, QUERY_META, emb_channels=hidden_dim, **kwargs)
+        else:  # hetero_graph = False (ablation_gnns.py): the un-converted homogeneous SAGE model on both sides
+            from .gnn_model import HOMOG_META
+
+            self.emb_model = BaseGNN(input_dim, hidden_dim, hidden_dim, args, HOMOG_META, emb_channels=hidden_dim, **kwargs)
+            self.emb_model_query = BaseGNN(input_dim, hidden_dim, hidden_dim, args, HOMOG_META, emb_channels=hidden_dim, **kwargs)
         self.count_model = nn.Sequential(nn.Linear(2 * hidden_dim, 4 * hidden_dim), nn.LeakyReLU(), nn.Linear(4 * hidden_dim, 1))
         # the reference collates DataLoader batches of args.batch_size neighborhoods (config.py:255): the default unit over
         # which SAGEConv's remove_self_loops quirk is evaluated (set_pyg_batch_size changes it)
@@ -123,6 +129,8 @@ class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
 
     # ---- the reference converts with pyg.nn.to_hetero at run time; these modules are built hetero ----
     def to_hetero_old(self, tconv_target=False, tconv_query=False):
+        if not getattr(self.args, "use_hetero", True):
+            raise RuntimeError("a use_hetero=False model is not converted (main.py calls to_hetero only when args.use_hetero)")
         if not (tconv_target and tconv_query):
             raise NotImplementedError("only the default SHMP (use_tconv=True) metadata is a CUDA path")
         return self
@@ -134,8 +142,8 @@ class NeighborhoodCountingModel(_PackedWeightsMixin, nn.Module):
 
     def on_load_checkpoint(self, checkpoint) -> None:
         a = checkpoint["hyper_parameters"]["args"]
-        if not (a.use_hetero and a.use_tconv and getattr(a, "use_canonical", True)):
-            raise NotImplementedError("checkpoint was trained without hetero/tconv/canonical: not a CUDA path")
+        if a.use_hetero and not (a.use_tconv and getattr(a, "use_canonical", True)):
+            raise NotImplementedError("checkpoint was trained with hetero but without tconv/canonical: not a CUDA path")
 
     load_from_checkpoint = classmethod(_load_lightning_checkpoint)
 

@@ -159,7 +159,9 @@ int desco_shmp_edge_types(const int32_t* edge_ptr, const int32_t* edge_col, int3
  *
  * Input: a packed batch (see desco_partition_fill).  hetero = 1: target neighborhoods (node types count/canonical,
  * canonical = last row of each neighborhood, 6 relations); hetero = 0: query graphs (one node type, 2 relations, no
- * anchor_mlp).  pyg_batch_size: size of the collated PyG batches the reference would have formed (config.py:255,
+ * anchor_mlp); hetero = 2: the homogeneous model of hetero_graph = False (workload.py:238-241, gnn_model.py:74-83): one
+ * node type, the last row of every neighborhood is the centre (node_feature = 1 in `feat`) whose embedding goes through
+ * anchor_mlp before the all-rows pooling (fp32 and multi-tile paths).  pyg_batch_size: size of the collated PyG batches the reference would have formed (config.py:255,
  * default 512; 0 = the whole input is one batch; < 0 = do not reproduce the quirk) - needed only to reproduce
  * SAGEConv's remove_self_loops on the bipartite relations (gnn_model.py:389-390), see DESIGN.md "reference quirks":
  * the dropped edge joins the canonical node and the FIRST count node of the neighborhood, which here is the lowest

@@ -191,6 +191,91 @@ def test_multi_tile_path_hub_rows_and_query_graphs(cuda_device):
     assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_homogeneous_model_matches_the_reference_golden(cuda_device, golden_dir, precision):
+    """hetero_graph=False (workload.py:238-241, ablation_gnns.py): canonical-mode neighborhoods, the un-converted SAGE
+    BaseGNN with anchor_mlp on the centre row (gnn_model.py:74-83).  sage_homog_ref.npz holds the output of the reference's
+    own BaseGNN run on the PyG stand-in; same seed -> same weights (construction order and state-dict keys are the
+    reference's)."""
+    from desco_b200.data import NeighborhoodBatch
+    from desco_b200.gnn_model import HOMOG_META, BaseGNN
+    from desco_b200.lightning_model import default_neighborhood_args
+
+    z = np.load(os.path.join(golden_dir, "sage_homog_ref.npz"))
+    torch.manual_seed(int(z["seed"]))
+    base = BaseGNN(1, 64, 64, default_neighborhood_args(use_hetero=False), HOMOG_META)
+    assert list(base.state_dict().keys()) == [str(k) for k in z["keys"]]
+    ck = float(sum(v.double().abs().sum() for v in base.state_dict().values()))
+    assert abs(ck - float(z["checksum"])) < 1e-6 * abs(ck)
+    base = base.cuda().eval()
+    base.precision = precision
+    batch = NeighborhoodBatch.from_numpy({k: z[k] for k in ("nbh_ptr", "node_gid", "edge_ptr", "edge_col", "edge_tri", "centre")},
+                                         hetero=False)
+    batch._cache["centre_last"] = True  # what partition_batch(mode="canonical") sets: the centre is the last, marked row
+    with torch.no_grad():
+        out = base(batch).cpu()
+    ref = torch.from_numpy(z["out"])
+    assert ((out - ref).abs() / ref.abs().clamp(min=1.0)).max().item() <= TOL
+    batch._cache["centre_last"] = False  # without the marked centre (query graphs) anchor_mlp touches no row: other numbers
+    with torch.no_grad():
+        plain = base(batch).cpu()
+    assert (plain - ref).abs().max().item() > 1e-3
+
+
+def test_homogeneous_counting_model_end_to_end(cuda_device):
+    """NeighborhoodCountingModel(use_hetero=False): canonical-mode partition -> homogeneous SHMP -> count head vs the oracle
+    core with one node type and one relation."""
+    from types import SimpleNamespace
+
+    from desco_b200.data import DeviceCSR, partition_batch
+    from desco_b200.lightning_model import STANDARD_QUERY_IDS, NeighborhoodCountingModel, default_neighborhood_args
+    from oracle import model as M
+    from oracle import partition as P
+
+    torch.manual_seed(9)
+    pm = NeighborhoodCountingModel(args=default_neighborhood_args(use_hetero=False)).eval().cuda()
+    pm.set_queries(STANDARD_QUERY_IDS[:8], hetero=False)
+    csr = gen_enzymes_shaped(seed=2, num_graphs=12)
+    batch = partition_batch(DeviceCSR.from_host(csr), None, 3, "canonical")
+    ref_b = P.partition_dataset(csr, 3, mode="canonical")
+    for k in ("nbh_ptr", "node_gid", "edge_ptr", "edge_col", "centre"):
+        assert np.array_equal(batch.to_numpy()[k], ref_b[k]), k
+    meta = (["n"], [("n", "r", "n")])
+
+    def oracle_emb(base, b, mark_centre):
+        oc = M.BaseGNN(1, 64, 64, M.default_args(use_hetero=False), meta).eval()
+        sd = base.state_dict()
+        osd = oc.state_dict()
+        for k in osd:  # oracle keys carry the single type / relation name; the homogeneous model's do not
+            src = k.replace(".n__r__n.", ".").replace(".n.", ".")
+            osd[k] = sd[src].cpu()
+        oc.load_state_dict(osd)
+        V, G = int(b["nbh_ptr"][-1]), len(b["nbh_ptr"]) - 1
+        dst = torch.repeat_interleave(torch.arange(V), torch.as_tensor(np.diff(b["edge_ptr"]), dtype=torch.long))
+        src_ = torch.as_tensor(b["edge_col"], dtype=torch.long)
+        bvec = torch.repeat_interleave(torch.arange(G), torch.as_tensor(np.diff(b["nbh_ptr"]), dtype=torch.long))
+        nf = torch.zeros(V, 1)
+        rows = torch.as_tensor(b["nbh_ptr"][1:] - 1, dtype=torch.long)
+        if mark_centre:
+            nf[rows] = 1.0
+        with torch.no_grad():
+            emb = oc.gnn_core({"n": nf}, {("n", "r", "n"): torch.stack([src_, dst])})["n"]
+            if mark_centre:
+                emb[rows] = oc.anchor_mlp(emb[rows])
+            return oc.post_mp(torch.zeros(G, emb.shape[1]).index_add_(0, bvec, emb))
+
+    qb = M.query_batch(STANDARD_QUERY_IDS[:8])
+    t = oracle_emb(pm.emb_model, ref_b, True)
+    q = oracle_emb(pm.emb_model_query, qb, False)
+    cm = pm.count_model.cpu()
+    with torch.no_grad():
+        want = torch.cat([cm(torch.cat((t, qq.expand_as(t)), -1)) for qq in q], -1)
+    pm.count_model.cuda()
+    with torch.no_grad():
+        got = pm.graph_to_pred(batch).cpu()
+    assert ((got - want).abs() / want.abs().clamp(min=1.0)).max().item() <= TOL
+
+
 def test_shmp_bf16_single_pass_variant(cuda_device):
     """The separately-stated bf16 variant (one tensor-core pass): 1e-2."""
     from oracle import partition as P
