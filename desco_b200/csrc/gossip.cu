@@ -101,6 +101,28 @@ __device__ __forceinline__ size_t s4_index(int i, int q, int Q, int QG, long lon
   return (size_t)q0 * (size_t)n_rows + (size_t)i * qc + (q - q0);
 }
 
+// hub rows of the layer-0 sweep: a power-law target has rows of 10^4 neighbours, which one warp walks in milliseconds -
+// invisible on one GPU, the whole tail of the kernel once the rows are sharded 8 ways.  The sweep parks such rows here
+// and a second kernel gives each of them a whole CTA.  (One list per device: launches of this library on different
+// streams of one device must not overlap in the gossip forward.)
+constexpr int L0_HUB_DEG = 2048;
+constexpr int L0_HUB_CAP = 8192;
+__device__ int g_l0_hub_count;
+__device__ int g_l0_hub_rows[L0_HUB_CAP];
+
+__device__ __forceinline__ void layer0_store(int i, int q, int Q, int QG, long long n_rows, const float* __restrict__ x,
+                                             const float* __restrict__ qvec, float4* __restrict__ S4, int d_lt, int deg,
+                                             float s_lt, float s_gt) {
+  const float g0 = qvec[(size_t)q * QV + 3 * F], g1 = qvec[(size_t)q * QV + 3 * F + 1];
+  const float dl = (float)d_lt, dg = (float)(deg - d_lt);
+  float4 o;
+  o.x = g0 * dl + (1.f - g0) * dg;      // dmix (layer 0)
+  o.y = g0 * s_lt + (1.f - g0) * s_gt;  // smix (layer 0)
+  o.z = x[(size_t)i * Q + q];           // c_i
+  o.w = g1 * dl + (1.f - g1) * dg;      // dmix (layer 1)
+  S4[s4_index(i, q, Q, QG, n_rows)] = o;
+}
+
 // layer 0: scalar gated SpMV for all queries; one warp per node, lane = query
 __global__ void gossip_layer0_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int node_begin,
                                      int node_end, const float* __restrict__ x, int Q, const float* __restrict__ qvec,
@@ -109,6 +131,15 @@ __global__ void gossip_layer0_kernel(const int32_t* __restrict__ rowptr, const i
   if (i >= node_end) return;
   const int lane = lane_id();
   const int eb = rowptr[i], ee = rowptr[i + 1];
+  if (ee - eb > L0_HUB_DEG) {  // park the row for gossip_layer0_hub_kernel (if the list is full it is walked here after all)
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(&g_l0_hub_count, 1);
+    slot = __shfl_sync(FULL_MASK, slot, 0);
+    if (slot < L0_HUB_CAP) {
+      if (lane == 0) g_l0_hub_rows[slot] = i;
+      return;
+    }
+  }
   for (int q0 = 0; q0 < Q; q0 += 32) {
     const int q = q0 + lane;
     float s_lt = 0.f, s_gt = 0.f;
@@ -126,15 +157,51 @@ __global__ void gossip_layer0_kernel(const int32_t* __restrict__ rowptr, const i
         if (j < i) s_lt += c; else s_gt += c;
       }
     }
-    if (q < Q) {
-      const float g0 = qvec[(size_t)q * QV + 3 * F], g1 = qvec[(size_t)q * QV + 3 * F + 1];
-      const float dl = (float)d_lt, dg = (float)(ee - eb - d_lt);
-      float4 o;
-      o.x = g0 * dl + (1.f - g0) * dg;      // dmix (layer 0)
-      o.y = g0 * s_lt + (1.f - g0) * s_gt;  // smix (layer 0)
-      o.z = x[(size_t)i * Q + q];           // c_i
-      o.w = g1 * dl + (1.f - g1) * dg;      // dmix (layer 1)
-      S4[s4_index(i, q, Q, QG, n_rows)] = o;
+    if (q < Q) layer0_store(i, q, Q, QG, n_rows, x, qvec, S4, d_lt, ee - eb, s_lt, s_gt);
+  }
+}
+
+// one CTA per parked hub row: the warps take 32-neighbour chunks round robin, partial sums are added in warp order
+constexpr int L0H_THREADS = 512;
+__global__ void __launch_bounds__(L0H_THREADS) gossip_layer0_hub_kernel(const int32_t* __restrict__ rowptr,
+                                                                       const int32_t* __restrict__ col,
+                                                                       const float* __restrict__ x, int Q,
+                                                                       const float* __restrict__ qvec,
+                                                                       float4* __restrict__ S4, int QG, long long n_rows) {
+  constexpr int NWH = L0H_THREADS / 32;
+  __shared__ float s_part[NWH][2][32];
+  __shared__ int s_dlt[NWH];
+  const int nh = min(g_l0_hub_count, L0_HUB_CAP);
+  const int lane = lane_id(), warp = warp_id();
+  for (int h = blockIdx.x; h < nh; h += gridDim.x) {
+    const int i = g_l0_hub_rows[h];
+    const int eb = rowptr[i], ee = rowptr[i + 1];
+    for (int q0 = 0; q0 < Q; q0 += 32) {
+      const int q = q0 + lane;
+      float s_lt = 0.f, s_gt = 0.f;
+      int d_lt = 0;
+      for (int base = eb + 32 * warp; base < ee; base += 32 * NWH) {
+        const int myj = (base + lane < ee) ? col[base + lane] : 0x7fffffff;
+        const int n = min(32, ee - base);
+        d_lt += __popc(__ballot_sync(FULL_MASK, myj < i));
+#pragma unroll 8
+        for (int k = 0; k < n; ++k) {
+          const int j = __shfl_sync(FULL_MASK, myj, k);
+          const float c = (q < Q) ? __ldg(x + (size_t)j * Q + q) : 0.f;
+          if (j < i) s_lt += c; else s_gt += c;
+        }
+      }
+      s_part[warp][0][lane] = s_lt;
+      s_part[warp][1][lane] = s_gt;
+      if (lane == 0) s_dlt[warp] = d_lt;
+      __syncthreads();
+      if (warp == 0 && q < Q) {
+        float a = 0.f, b = 0.f;
+        int d = 0;
+        for (int w = 0; w < NWH; ++w) { a += s_part[w][0][lane]; b += s_part[w][1][lane]; d += s_dlt[w]; }
+        layer0_store(i, q, Q, QG, n_rows, x, qvec, S4, d, ee - eb, a, b);
+      }
+      __syncthreads();
     }
   }
 }
@@ -806,10 +873,15 @@ int desco_gossip_layer0_grouped(const int32_t* rowptr, const int32_t* col, int32
   if (node_end == node_begin || num_queries == 0) return DESCO_OK;
   if (!rowptr || !col || !x || !qvec || !s4) return DESCO_EINVAL;
   const long long threads = (long long)(node_end - node_begin) * 32;
-  DescoProfScope prof(DESCO_PROF_GOSSIP_L0, (cudaStream_t)stream);
+  void* hub_count = nullptr;
+  DESCO_CUDA_TRY(cudaGetSymbolAddress(&hub_count, g_l0_hub_count));
+  DESCO_CUDA_TRY(cudaMemsetAsync(hub_count, 0, sizeof(int), (cudaStream_t)stream));
+  DescoProfScope prof(DESCO_PROF_GOSSIP_L0, (cudaStream_t)stream, 2);
   gossip_layer0_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       rowptr, col, node_begin, node_end, x, num_queries, qvec, reinterpret_cast<float4*>(s4), group_size,
       (long long)s4_rows);
+  gossip_layer0_hub_kernel<<<2 * desco_num_sms(), L0H_THREADS, 0, (cudaStream_t)stream>>>(
+      rowptr, col, x, num_queries, qvec, reinterpret_cast<float4*>(s4), group_size, (long long)s4_rows);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;
 }

@@ -145,3 +145,28 @@ def test_gossip_sharded_node_ranges_equal_full(cuda_device, precision):
                                        PRECISION[precision], _ptr(stage), sb, st) == 0
     torch.cuda.synchronize()
     assert torch.equal(out, full)
+
+
+def test_gossip_hub_rows_take_the_whole_cta_paths(cuda_device, precision):
+    """A node with 5000 neighbours: parked by the layer-0 sweep for gossip_layer0_hub_kernel (> 2048 neighbours) and gathered
+    by the whole CTA in layer 1 (> 512); its leaves see it as their only neighbour.  fp64 oracle: the literal fp32 index_add
+    over 5000 messages is itself off by more than the tolerance."""
+    import networkx as nx
+
+    from desco_b200.graph import csr_from_networkx
+
+    om, pm = _pair(14, precision)
+    g = nx.gnm_random_graph(6000, 9000, seed=3)
+    g.add_edges_from((2500, v) for v in range(6000) if v != 2500 and v % 6 != 0)
+    csr = csr_from_networkx([g])
+    assert np.diff(csr.rowptr).max() > 4096
+    gen = torch.Generator().manual_seed(2)
+    Q = 5
+    x = torch.floor(torch.exp(torch.randn(csr.num_nodes, Q, generator=gen)))
+    qe = torch.randn(Q, 64, generator=gen)
+    om = om.double()
+    om.set_query_emb(qe.double())
+    with torch.no_grad():
+        ref = om.graph_to_count(x.double(), torch.from_numpy(csr.edge_index())).float()
+    out = _run(pm, csr, x, qe)
+    assert _rel(out, ref) <= TOL
