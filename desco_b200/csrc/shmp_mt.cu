@@ -29,7 +29,11 @@ constexpr int KB = 3;                        // 64-wide K blocks: tri | tride | 
 constexpr int THREADS = 512;
 constexpr int NW = THREADS / 32;             // 16 warps x 128 registers (16 row loads in flight each); rows of a tile are dealt by a ticket
 constexpr int EPI_WARPS = 16;                // the warps that run the epilogue (4 lane quarters x 4 column groups)
-constexpr int HUB_DEG = 1024;                // rows with more edges are gathered by the whole CTA
+constexpr int MID_DEG = 96;                  // rows with more edges are gathered by a GROUP of 4 warps (ncu: 41 % of the stall
+                                             // samples sat at the barrier behind the one warp that drew a long row) ...
+constexpr int HUB_DEG = 2048;                // ... and beyond this by the whole CTA
+constexpr int GW = 4;                        // warps per group
+constexpr int NG = 4;                        // groups per CTA
 constexpr int IMG = TR * 128;                // one bf16 image of a [128 x 64] block
 constexpr int B_IMG = F * 128;               // one bf16 image of a [64 n x 64 k] weight block
 constexpr int SM_B = 0;                                  // [KB][hi | lo] weight images, 48 KB
@@ -37,8 +41,8 @@ constexpr int SM_A = SM_B + KB * 2 * B_IMG;              // [KB][hi | lo] operan
 constexpr int SM_ROW = SM_A + KB * 2 * IMG;              // 2 x { int s_row, s_g, s_code, s_eb, s_ee [TR] }
 constexpr int SM_HUB = SM_ROW + 2 * 5 * TR * 4;          // float4 s_hub[NW][16][2]
 constexpr int SM_BIAS = SM_HUB + NW * 16 * 32;           // float bias[64]
-constexpr int SM_BARS = SM_BIAS + F * 4;                 // 2 mbarriers, tmem slot, hub count, 2 row tickets, hub list
-constexpr int SM_TOTAL = SM_BARS + 64 + TR;
+constexpr int SM_BARS = SM_BIAS + F * 4;                 // 2 mbarriers, tmem slot, hub / mid counts, tickets, hub list, mid list
+constexpr int SM_TOTAL = SM_BARS + 64 + 2 * TR;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 static_assert(SM_A % 1024 == 0 && B_IMG % 1024 == 0 && IMG % 1024 == 0, "UMMA tiles must be 1024-B aligned");
 static_assert(SMEM_BYTES <= 232448, "multi-tile SHMP kernel exceeds the 227 KB shared-memory limit");
@@ -129,7 +133,11 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   int* s_nhub = reinterpret_cast<int*>(tmem_slot + 1);
   int* s_ticket = s_nhub + 1;  // [2], by tile parity
+  int* s_nmid = s_ticket + 2;
+  int* s_mid_ticket = s_nmid + 1;
+  int* s_grow = s_mid_ticket + 1;  // [NG] the row a group is working on
   uint8_t* s_hubs = reinterpret_cast<uint8_t*>(bars) + 64;
+  uint8_t* s_mids = s_hubs + TR;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int half = lane >> 4, l16 = lane & 15;
@@ -175,8 +183,10 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
     if (tid == TR) s_ticket[b] = 0;
   };
   setup(blockIdx.x, 0);
-  if (tid == 0) *s_nhub = 0;
+  if (tid == 0) { *s_nhub = 0; *s_nmid = 0; *s_mid_ticket = 0; }
   __syncthreads();
+  const int grp = warp / GW, gw = warp % GW;
+  auto group_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(32 * GW) : "memory"); };
   int buf = 0;
 
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, buf ^= 1) {
@@ -200,15 +210,41 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
       if (row >= 0) {
         if (half == 0) self = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)row * F) + l16);
         const int eb = t_eb[r], ee = t_ee[r];
-        hub = ee - eb > HUB_DEG;
+        hub = ee - eb > MID_DEG;
         if (!hub) gather_edges(p.h_in, p.edge_col, p.edge_tri, eb, ee, 0, 1, lane, at, ad);
-        else if (lane == 0) s_hubs[atomicAdd(s_nhub, 1)] = (uint8_t)r;
+        else if (lane == 0) {
+          if (ee - eb > HUB_DEG) s_hubs[atomicAdd(s_nhub, 1)] = (uint8_t)r;
+          else s_mids[atomicAdd(s_nmid, 1)] = (uint8_t)r;
+        }
       }
       if (!hub) store_quad(sA + (half ? 2 * IMG : 0), r, l16, half ? ad : at);  // the two halves write one block each
       if (half == 0) store_quad(sA + 4 * IMG, r, l16, self);
     }
     __syncthreads();  // every warp is past the previous tile's epilogue here: the other metadata buffer is free
     setup(tile + gridDim.x, buf ^ 1);
+    // mid rows: dealt by a ticket to the 4 groups of 4 warps; a group's warps take the row's 32-edge chunks round robin and
+    // its first warp adds the four partial sums in warp order (deterministic), so long rows proceed four at a time
+    for (const int nmid = *s_nmid;;) {
+      if ((tid & (32 * GW - 1)) == 0) s_grow[grp] = atomicAdd(s_mid_ticket, 1);
+      group_bar();
+      const int t = s_grow[grp];
+      if (t >= nmid) break;
+      const int r = s_mids[t];
+      float4 at = make_float4(0.f, 0.f, 0.f, 0.f), ad = at;
+      gather_edges(p.h_in, p.edge_col, p.edge_tri, t_eb[r], t_ee[r], gw, GW, lane, at, ad);
+      if (half == 0) {
+        s_hub[(warp * 16 + l16) * 2] = at;
+        s_hub[(warp * 16 + l16) * 2 + 1] = ad;
+      }
+      group_bar();
+      if (gw == 0) {
+        float4 tt = s_hub[(warp * 16 + l16) * 2 + half];  // half 0 sums the triangle partials, half 1 the tride partials
+        for (int w = 1; w < GW; ++w) add4(tt, s_hub[((warp + w) * 16 + l16) * 2 + half]);
+        store_quad(sA + (half ? 2 * IMG : 0), r, l16, tt);
+      }
+      group_bar();
+    }
+    __syncthreads();  // (s_hub is shared with the whole-CTA pass below)
     for (int hh = 0, nh = *s_nhub; hh < nh; ++hh) {  // hub rows: 32-edge chunks dealt over all warps, summed in warp order
       const int r = s_hubs[hh], row = t_row[r];
       float4 at = make_float4(0.f, 0.f, 0.f, 0.f), ad = at;
@@ -232,8 +268,9 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_mt_layer_kernel(const MtArgs 
 
     // ---- [128 x 192] . [192 x 64] on tcgen05: hi.hi + lo.hi + hi.lo ----
     if (tid == 0) {
-      *s_nhub = 0;  // every thread has read the hub count (barrier above); the next tile's gather, which pushes its hubs,
-                    // starts only after the MMA issued below has completed
+      *s_nhub = 0;  // every thread has read the hub / mid counts (barrier above); the next tile's gather, which pushes its
+      *s_nmid = 0;  // long rows, starts only after the MMA issued below has completed
+      *s_mid_ticket = 0;
       if (!weights_ready) {
         if (!tc05::mbar_wait(&bars[0], 0)) { atomicExch(p.status, DESCO_ECUDA); __trap(); }
         weights_ready = true;
