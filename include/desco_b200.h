@@ -414,8 +414,10 @@ int desco_train_adam(float* p, const float* g, float* m, float* v, int64_t n, fl
                      float eps, float weight_decay, int32_t step, void* stream);
 
 /* Phase profile of the fused SHMP layer kernel (measurement support, no reference counterpart): clock64 cycles summed
- * over all CTAs since the last reset, as seen by thread 0 of each CTA.  out[7] = {tile setup, pool + canonical inputs,
- * weight wait + MMA issue, canonical rows on the CUDA cores, wait for the MMA, TMEM -> shared memory, gather}. */
+ * over all CTAs since the last reset, as seen by thread 0 of each CTA; counted only by the instantiation that is launched
+ * when DESCO_FUSED_PHASE_TIMING=1 is in the environment (the production kernel carries no counters).  out[8] = {tile
+ * setup, pool stage A up to its barrier, weight prefetch of warp 0, canonical rows (mma.sync), wait for the MMA,
+ * TMEM -> shared memory, gather, pool stage B up to its barrier}. */
 int desco_shmp_fused_phase_cycles(uint64_t* out, int32_t reset);
 
 /* ------------------------------------------------------------------------------------------------------------------
