@@ -11,12 +11,19 @@
 //   1. transform-then-aggregate (SAGEConv is linear, so sum_j (h_j W) == (sum_j h_j) W):
 //        P = h . [W_tri | W_tride | W_self]           128 x 64 x 192 GEMM on tcgen05, bf16 hi/lo operand split
 //      (three passes hi.hi + lo.hi + hi.lo, fp32 accumulation in TMEM: ~3e-6 from the fp32 oracle), weights fetched
-//      with one bulk async copy per image; the next layer's weights stream in while this layer's epilogue runs;
-//   2. while the tensor pipe works, the CUDA cores do the few canonical rows of the tile in fp32:
+//      with one bulk async copy per image; the next layer's weights stream in while this layer's epilogue runs.  The
+//      issuing lane is held by the tensor pipe for the length of the 12 MMAs, so its warp sits the pool phase out;
+//   2. under the MMA, the other 15 warps pool: global_add_pool over the count rows and the canonical update's
+//      messages (sum of the rows with a tri / tride edge into the canonical row) as a two-stage fixed-order reduction
+//      (stage A: one quarter-warp per run of <= 4 rows; stage B: one thread per neighborhood and 4 features), h_a goes
+//      out (skip-concat) and the canonical inputs [sum_tri | sum_tride | h_a] are parked as bf16 hi/lo rows;
+//   3. the few canonical rows of the tile run on the warp-level tensor path (mma.sync m16n8k16, A fragments by
+//      ldmatrix, weights as host-packed B fragments, same three-pass split):
 //        h_a' = relu([sum_tri h_j | sum_tride h_j | h_a] . Wa + b_a),   cvec = h_a . [Cw_tri | Cw_tride];
-//   3. TMEM -> shared memory, then the segmented, edge-type-split gather runs out of shared memory:
+//   4. TMEM -> shared memory, then the segmented, edge-type-split gather runs out of shared memory, rows taken in
+//      descending degree order (counting sort per tile) so that the rows sharing a warp pad to similar lengths:
 //        h_i' = relu(P_self[i] + sum_{j in N_tri(i)} P_tri[j] + sum_{j in N_tride(i)} P_tride[j] + cvec[type(i,a)] + b);
-//   4. h' is written back as the next layer's bf16 hi/lo A operand (swizzled) and as fp32 rows for pooling.
+//   5. h' is written back as the next layer's bf16 hi/lo A operand (swizzled) and as fp32 rows for pooling.
 // Only the pooled sums and the canonical rows ([G, (L+1)*64] each) ever leave the chip.
 #include <stdlib.h>
 #include "common.cuh"
@@ -83,7 +90,8 @@ static_assert(SM_AHI % 1024 == 0 && SM_ALO % 1024 == 0 && SM_BLO % 1024 == 0, "U
 static_assert(SM_CIN % 16 == 0 && (CINP * 2) % 16 == 0 && SM_BARS % 8 == 0, "ldmatrix rows / mbarriers");
 static_assert(ZERO_OFF + 2 * F <= 65535, "edge records are 16-bit float offsets");
 // pooling work items (<= 4 count rows of one neighborhood each): sum ceil(n_i / 4) <= (TR - nc) / 4 + 3 nc / 4
-static_assert(MAXC < 32 && TR / 4 + (3 * MAXC + 3) / 4 <= 64 && 16 * MAXC + 8 * MAXC <= THREADS, "pool phase thread / item budget");
+static_assert(MAXC < 32 && TR / 4 + (3 * MAXC + 3) / 4 <= (NWARPS - 1) * 4 && 16 * MAXC + 8 * MAXC <= THREADS - 32,
+              "pool phase thread / item budget (15 warps: the issuing warp does not take part)");
 static_assert(64 * 3 * F * 4 <= TR * LDP * 4, "the pooling partials alias the (dead) P buffer");
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(1024) shmp_tile_plan_kernel(const int32_t* __r
 // fused layers
 // ------------------------------------------------------------------------------------------------------------------
 // phase timing (thread 0 of every CTA accumulates its own clock64 deltas; read with desco_shmp_fused_phase_cycles)
-enum { PH_SETUP = 0, PH_POOL, PH_ISSUE, PH_CANON, PH_WAIT_MMA, PH_T2S, PH_GATHER, PH_POOLB, PH_COUNT };
+enum { PH_SETUP = 0, PH_POOL, PH_ISSUE, PH_CANON, PH_WAIT_MMA, PH_T2S, PH_GATHER, PH_POOLB, PH_ISSUER_WAIT, PH_ISSUER_MMA, PH_COUNT };
 __device__ unsigned long long g_phase_cycles[PH_COUNT];
 
 struct FusedArgs {
@@ -191,6 +199,15 @@ __device__ __forceinline__ void add4(float4& a, const float4 b) {
       "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%6, %7};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%2, %3}, ra;\n\t}"
       : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)
       : "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w));
+}
+// a += b * m as two packed fp32x2 FMAs
+__device__ __forceinline__ void fma4(float4& a, const float4 b, const float m) {
+  asm("{\n\t.reg .b64 ra, rb, rm;\n\t"
+      "mov.b64 rm, {%8, %8};\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%4, %5};\n\tfma.rn.f32x2 ra, rb, rm, ra;\n\tmov.b64 {%0, %1}, ra;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%6, %7};\n\tfma.rn.f32x2 ra, rb, rm, ra;\n\tmov.b64 {%2, %3}, ra;\n\t}"
+      : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w)
+      : "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "f"(m));
 }
 __device__ __forceinline__ uint32_t bf2_bits(const __nv_bfloat162 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 // four fp32 -> bf16 hi / lo pairs with the packed converts (x = hi + lo + O(2^-17 |x|), as tc05::split_bf16)
@@ -287,6 +304,28 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
   const int hw = lane >> 4, hl = lane & 15;  // half-warp id / lane inside the half-warp (layer-0 inputs)
   const int rw = lane >> 3, q = lane & 7;    // quarter-warp id / lane inside the quarter (gathers: one quarter per row)
   const int fg = lane >> 2, ft = lane & 3;   // mma fragment coordinates: group (row / column), thread in group
+
+  // this warp's B fragments of the canonical-row weights of a layer (warps 0-7: z_a column tile `warp`, K = 192, 12
+  // k-steps; warps 8-15: cvec column tiles 2(warp-8), 2(warp-8)+1, K = 64, 4 k-steps each) and its bias: requested at the
+  // start of the layer, consumed after the pool phase.  (80 KB per tile and layer through the load/store path; when
+  // they are requested makes no difference to the kernel time - measured at the layer start, in instalments over the
+  // pool phase, and one layer ahead spread over the TMEM read-out and the gather: 0.240 ms each - because the L1
+  // wavefront pipe, shared with all the shared-memory traffic, is the busiest unit either way.)
+  uint4 wf[12];
+  float2 bias_a = make_float2(0.f, 0.f);
+  auto fetch_frags = [&](int layer) {
+    const uint8_t* wl = p.w_layers + (size_t)layer * LAYER_BYTES;
+    if (warp < 8) {
+      bias_a = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(wl + OFF_BIASA) + 8 * warp + 2 * ft));
+      const uint4* W = reinterpret_cast<const uint4*>(wl + OFF_WAT) + (size_t)warp * 12 * 32 + lane;
+#pragma unroll
+      for (int ks = 0; ks < 12; ++ks) wf[ks] = __ldg(W + 32 * ks);
+    } else {
+      const uint4* W = reinterpret_cast<const uint4*>(wl + OFF_CWT) + (size_t)(2 * (warp - 8)) * 4 * 32 + lane;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) wf[ks] = __ldg(W + 32 * ks);
+    }
+  };
 
   while (cur_tile < total_tiles) {
     {
@@ -431,7 +470,9 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
         // ------------ tensor pipe: P = h . [W_tri | W_tride | W_self], issued first so that it runs under the pool
         // and canonical phases ------------
         if (l < p.layers && tid == ISSUER) {
+          const long long t_w0 = TIMED ? clock64() : 0;
           if (!tc05::mbar_wait(&bars[0], wphase)) timed_out = true;
+          const long long t_w1 = TIMED ? clock64() : 0;
           copy_pending = false;
           tc05::fence_after_sync();
           const uint64_t dAhi = tc05::make_smem_desc(sAhi), dAlo = tc05::make_smem_desc(sAlo);
@@ -447,36 +488,24 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
             }
           }
           tc05::mma_commit(&bars[1]);
+          if (TIMED) {
+            atomicAdd(&g_phase_cycles[PH_ISSUER_WAIT], (unsigned long long)(t_w1 - t_w0));
+            atomicAdd(&g_phase_cycles[PH_ISSUER_MMA], (unsigned long long)(clock64() - t_w1));
+          }
         }
         if (l < p.layers) wphase ^= 1;
-        // this warp's B fragments of the canonical-row weights of layer l: issued now, consumed after the pool phase.
-        // Warps 0-7: z_a column tile `warp` (K = 192, 12 k-steps); warps 8-15: cvec column tiles 2(warp-8), 2(warp-8)+1
-        // (K = 64, 4 k-steps each).
-        const uint8_t* wl = p.w_layers + (size_t)(l < p.layers ? l : 0) * LAYER_BYTES;
-        uint4 wf[12];
-        // biases of this layer, fetched here too so that their L2 latency hides under the pool phase
-        float2 bias_a = make_float2(0.f, 0.f);
-        if (l < p.layers) {
-          if (!bias_resident && tid < F) sBiasC[tid] = __ldg(reinterpret_cast<const float*>(wl + OFF_BIASC) + tid);  // read after two barriers
-          if (warp < 8) bias_a = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(wl + OFF_BIASA) + 8 * warp + 2 * ft));
-        }
-        // (the fragment loads are issued in three instalments - here, after the stage-A barrier and before the stage-B
-        //  barrier: 96 KB requested at once by the CTA saturates the load queue and stalls every warp)
-        const uint4* Wfrag = (warp < 8) ? reinterpret_cast<const uint4*>(wl + OFF_WAT) + (size_t)warp * 12 * 32 + lane
-                                        : reinterpret_cast<const uint4*>(wl + OFF_CWT) + (size_t)(2 * (warp - 8)) * 4 * 32 + lane;
-        const int nfrag = (l < p.layers) ? (warp < 8 ? 12 : 8) : 0;
-        auto fetch_frags = [&](int k0) {
-#pragma unroll
-          for (int ks = 0; ks < 12; ++ks)
-            if (ks >= k0 && ks < k0 + 4 && ks < nfrag) wf[ks] = __ldg(Wfrag + 32 * ks);
-        };
-        fetch_frags(0);
+        if (l < p.layers) fetch_frags(l);
+        if (!bias_resident && l < p.layers && tid < F)  // read after two barriers
+          sBiasC[tid] = __ldg(reinterpret_cast<const float*>(p.w_layers + (size_t)l * LAYER_BYTES + OFF_BIASC) + tid);
         lap(PH_ISSUE);
         // ------------ pool + canonical inputs of layer l (from the fp32 rows of h^l in sStage, h_a^l in sCh) ------------
         // stage A: one quarter-warp per work item (<= 4 rows): partial sums of the rows (global_add_pool, gnn_model.py:107)
         // and of the rows with a tri / tride edge into the canonical row (the canonical update's messages); fixed order
+        // (the last warp sits the pool phase out: its lane 0 is held by the tensor pipe for the length of the 12 MMAs it
+        //  issues - tcgen05.mma issue blocks until the pipe accepts the instruction - and would make every stage-A
+        //  barrier wait ~1.2 k cycles; stages A and B fit the other 15 warps and meet at a named barrier)
         float* sPart = sP;  // [item][pool 64 | tri 64 | tride 64]; the P buffer is dead between the gather and the next T2S
-        {
+        if (warp < NWARPS - 1) {
           const int item = warp * 4 + rw;
           if (item < sItemBase[nc]) {
             const int it = sItem[item], r0 = it & 255, cnt = it >> 8;
@@ -489,8 +518,10 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
                 const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 32);
                 const int cin = sCanIn[r0 + j];
                 add4(p0, v0); add4(p1, v1);
-                if (cin == 1) { add4(t0, v0); add4(t1, v1); }
-                if (cin == 2) { add4(d0, v0); add4(d1, v1); }
+                // branch-free (the quarters of a warp disagree on cin, and a divergent branch per row cost ~200 cycles)
+                const float mt = cin == 1 ? 1.f : 0.f, md = cin == 2 ? 1.f : 0.f;
+                fma4(t0, v0, mt); fma4(t1, v1, mt);
+                fma4(d0, v0, md); fma4(d1, v1, md);
               }
             }
             float* dst = sPart + item * (3 * F) + 4 * q;
@@ -499,9 +530,8 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
             *reinterpret_cast<float4*>(dst + 2 * F) = d0; *reinterpret_cast<float4*>(dst + 2 * F + 32) = d1;
           }
         }
-        __syncthreads();
+        if (warp < NWARPS - 1) asm volatile("bar.sync 1, %0;" ::"n"(THREADS - 32) : "memory");
         lap(PH_POOL);
-        fetch_frags(4);
         if (l == 0 && tid < TR) sOrder[sHist[sort_key] + sort_pos] = (uint8_t)tid;  // gather order (read two barriers on)
         // stage B: (neighborhood, 4 features) sums its items in order; h_a^l goes out (skip-concat, gnn_model.py:275) and
         // joins the canonical inputs [sum_tri h_j | sum_tride h_j | h_a] as bf16 hi/lo rows
@@ -546,7 +576,6 @@ __global__ void __launch_bounds__(THREADS, 1) shmp_fused_kernel(const FusedArgs 
           }
         }
         if (l == p.layers) break;
-        fetch_frags(8);
         __syncthreads();
         lap(PH_POOLB);
 

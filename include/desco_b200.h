@@ -415,9 +415,10 @@ int desco_train_adam(float* p, const float* g, float* m, float* v, int64_t n, fl
 
 /* Phase profile of the fused SHMP layer kernel (measurement support, no reference counterpart): clock64 cycles summed
  * over all CTAs since the last reset, as seen by thread 0 of each CTA; counted only by the instantiation that is launched
- * when DESCO_FUSED_PHASE_TIMING=1 is in the environment (the production kernel carries no counters).  out[8] = {tile
+ * when DESCO_FUSED_PHASE_TIMING=1 is in the environment (the production kernel carries no counters).  out[10] = {tile
  * setup, pool stage A up to its barrier, weight prefetch of warp 0, canonical rows (mma.sync), wait for the MMA,
- * TMEM -> shared memory, gather, pool stage B up to its barrier}. */
+ * TMEM -> shared memory, gather, pool stage B up to its barrier; then, as seen by the issuing thread: wait for the layer's
+ * weight images, issue of the 12 tcgen05.mma}. */
 int desco_shmp_fused_phase_cycles(uint64_t* out, int32_t reset);
 
 /* ------------------------------------------------------------------------------------------------------------------

@@ -13,13 +13,13 @@ g = DeviceCSR.from_host(csr); c = torch.as_tensor(cen, dtype=torch.int32, device
 b = partition_batch(g, c, DEPTH)
 for _ in range(3): m.graph_to_count(b)
 torch.cuda.synchronize()
-out=(ctypes.c_uint64*8)()
+out=(ctypes.c_uint64*10)()
 lib.desco_shmp_fused_phase_cycles(out,1)
 N=10
 for _ in range(N): m.emb_model(b)
 torch.cuda.synchronize()
 lib.desco_shmp_fused_phase_cycles(out,1)
-names=['setup','poolA(+barrier)','issue(warp0)','canon','wait_mma','t2s','gather','poolB(+barrier)']
-tot=sum(out)
+names=['setup','poolA(+barrier)','issue(warp0)','canon','wait_mma','t2s','gather','poolB(+barrier)','issuer: weight wait','issuer: mma issue']
+tot=sum(out[:8])
 print("cycles per CTA per launch:", tot/148/N, "= us @1.965GHz", tot/148/N/1965)
 for n,v in zip(names,out): print(f"{n:9s} {v/148/N:10.0f} cyc/CTA/launch  {v/tot:.3f}")
