@@ -396,6 +396,25 @@ __global__ void __launch_bounds__(THREADS, 2) gossip_layer1_kernel(
 // The staging buffer is walked in chunks of tiles, so its size is bounded whatever the graph.
 // ------------------------------------------------------------------------------------------------------------------
 namespace gtc {
+// packed fp32x2 arithmetic (one issue slot for two lanes of the same operation; IEEE rounding as the scalar forms)
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 constexpr int TR = 128;
 constexpr int SLOT = 2 * TR * 128;               // one operand slot: hi (16 KB) | lo (16 KB)
 constexpr int TILE_CD = 2 * TR * 4;              // c[TR], d1[TR]
@@ -413,7 +432,7 @@ __global__ void __launch_bounds__(G_THREADS, 5) gossip_gather_kernel(
     long long tile0, uint8_t* __restrict__ stage) {
   __shared__ float4 s_slot[G_NW * 32];  // per-warp staging of 32 neighbours / per-warp partial sums of a hub row
   __shared__ uint8_t s_hubs[TR];
-  __shared__ int s_nhub;
+  __shared__ int s_nhub, s_next;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long tile = tile0 + blockIdx.x;
   const int q = (int)(tile % Q);
@@ -451,27 +470,44 @@ __global__ void __launch_bounds__(G_THREADS, 5) gossip_gather_kernel(
     }
     return f;
   };
+  // Packed form of x1_of for TWO neighbours at a time (sm_100 fp32x2 pipe: half the issue slots; the gather is issue
+  // bound): the warp's slot holds the neighbours' scalars as three arrays, so one broadcast 8-byte load brings the pair
+  // (x_k, x_k+1), and the lane's coefficients are kept as duplicated pairs.  Same operations in the same order per
+  // element as x1_of, and the same even / odd accumulation as before: results are bit-identical.
+  const float2 aX = make_float2(alpha.x, alpha.x), aY = make_float2(alpha.y, alpha.y);
+  const float2 bX = make_float2(beta.x, beta.x), bY = make_float2(beta.y, beta.y);
+  const float2 dX = make_float2(delta.x, delta.x), dY = make_float2(delta.y, delta.y);
+  const float2 gX = make_float2(gamma.x, gamma.x), gY = make_float2(gamma.y, gamma.y);
   auto consume = [&](const Fetch& f, int i, float2& lt, float2& gt) {
-    float4* slot = s_slot + warp * 32;
-    slot[lane] = f.s;
+    float* sl = reinterpret_cast<float*>(s_slot) + warp * 128;  // x[0..34) | y at +40 | z at +80 (8-byte aligned starts)
     const int n = f.n;
     const int nlt = __popc(__ballot_sync(FULL_MASK, f.j < i));
+    const int pos = lane + ((lane >= nlt) ? (nlt & 1) : 0);  // the j > i run starts on an even slot too
+    sl[pos] = f.s.x; sl[40 + pos] = f.s.y; sl[80 + pos] = f.s.z;
     __syncwarp();
-    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
-    int k = 0;
-    for (; k + 1 < nlt; k += 2) {
-      const float2 v0 = x1_of(slot[k]), v1 = x1_of(slot[k + 1]);
-      a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
-    }
-    if (k < nlt) { const float2 v = x1_of(slot[k]); a0.x += v.x; a0.y += v.y; }
-    lt.x += a0.x + a1.x; lt.y += a0.y + a1.y;
-    a0 = make_float2(0.f, 0.f); a1 = a0;
-    for (k = nlt; k + 1 < n; k += 2) {
-      const float2 v0 = x1_of(slot[k]), v1 = x1_of(slot[k + 1]);
-      a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y;
-    }
-    if (k < n) { const float2 v = x1_of(slot[k]); a0.x += v.x; a0.y += v.y; }
-    gt.x += a0.x + a1.x; gt.y += a0.y + a1.y;
+    auto run = [&](int k0, int k1, float2& acc) {  // neighbours in slots [k0, k1), k0 even
+      float2 ex = make_float2(0.f, 0.f), ey = ex;  // feature x / y of this lane, (even, odd) neighbours
+      int k = k0;
+#pragma unroll 2
+      for (; k + 1 < k1; k += 2) {
+        const float2 X = *reinterpret_cast<const float2*>(sl + k), Y = *reinterpret_cast<const float2*>(sl + 40 + k),
+                     Z = *reinterpret_cast<const float2*>(sl + 80 + k);
+        float2 vx = fma2(X, aX, fma2(Y, bX, fma2(Z, dX, gX)));
+        float2 vy = fma2(X, aY, fma2(Y, bY, fma2(Z, dY, gY)));
+        vx.x = fmaxf(vx.x, 0.f); vx.y = fmaxf(vx.y, 0.f); vy.x = fmaxf(vy.x, 0.f); vy.y = fmaxf(vy.y, 0.f);
+        ex = add2(ex, vx);
+        ey = add2(ey, vy);
+      }
+      if (k < k1) {
+        const float2 v = x1_of(make_float4(sl[k], sl[40 + k], sl[80 + k], 0.f));
+        ex.x += v.x; ey.x += v.y;
+      }
+      acc.x += ex.x + ex.y;
+      acc.y += ey.x + ey.y;
+    };
+    run(0, nlt, lt);
+    const int g0 = nlt + (nlt & 1);
+    run(g0, g0 + (n - nlt), gt);
     __syncwarp();
   };
   auto store_row = [&](uint8_t* img, int r, float2 v) {  // two features of row r as bf16 hi / lo, swizzled
@@ -482,12 +518,15 @@ __global__ void __launch_bounds__(G_THREADS, 5) gossip_gather_kernel(
     *reinterpret_cast<__nv_bfloat162*>(img + off) = h;
     *reinterpret_cast<__nv_bfloat162*>(img + TR * 128 + off) = l;
   };
-  if (tid == 0) s_nhub = 0;
+  if (tid == 0) { s_nhub = 0; s_next = G_NW; }
   __syncthreads();
 
-  // ---- x1_i and u_i = g1 * sum_{j<i} x1_j + (1-g1) * sum_{j>i} x1_j; one warp per row, hub rows deferred ----
+  // ---- x1_i and u_i = g1 * sum_{j<i} x1_j + (1-g1) * sum_{j>i} x1_j; one warp per row, hub rows deferred.  Rows are
+  // dealt by a ticket: degrees are power-law distributed, and with a static stride the warp that met the long rows kept
+  // the other seven waiting at the barrier below (22 % of the stall samples) ----
+  static_assert(GR == 1, "the row ticket hands out one row at a time");
 #pragma unroll 1
-  for (int r0 = warp; r0 < TR; r0 += G_NW * GR) {
+  for (int r0 = warp; r0 < TR;) {
     int eb[GR], ee[GR];
     bool hub[GR];
     Fetch f[GR];
@@ -535,6 +574,8 @@ __global__ void __launch_bounds__(G_THREADS, 5) gossip_gather_kernel(
         g_d1[r] = d1;
       }
     }
+    if (lane == 0) r0 = atomicAdd(&s_next, 1);
+    r0 = __shfl_sync(FULL_MASK, r0, 0);
   }
   __syncthreads();
   // ---- hub rows: 32-edge chunks dealt over all warps of the CTA, partial sums added in warp order ----
