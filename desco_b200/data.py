@@ -294,6 +294,54 @@ def partition_batches(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: 
         yield batch
 
 
+def partition_sizes(graph: DeviceCSR, centres: Optional[torch.Tensor], depth: int, mode: Union[int, str] = "hetero",
+                    large: Optional[bool] = None, max_centres: Optional[int] = None):
+    """Streaming count-only mode: rows and directed edges of every centre's canonical neighborhood, nothing emitted.
+
+    Only the count pass of the partition runs (``desco_partition_count`` / ``desco_partition_large_count``), chunk by
+    chunk, so a centre list of any length goes through in bounded memory - what a full sweep over a 10^7-node target
+    needs before anything is packed (the sizes decide the chunking: ``partition_batches``) and what the reference's
+    dataset statistics compute by building every neighborhood (``analysis/dataset_statistics.py:53`` ->
+    ``data.py:375-396``).  Returns (rows [C] int32, directed_edges [C] int32) in centre order; an edge-free
+    neighborhood - which ``NeighborhoodDataset.process`` drops, ``workload.py:253-256`` - reads (0, 0)."""
+    lib = _lib.load()
+    dev = graph.rowptr.device
+    if large is None:
+        large = graph.max_graph_nodes > LARGE_GRAPH_NODES
+    if isinstance(mode, str):
+        mode = {"hetero": MODE_HETERO, "canonical": MODE_CANONICAL, "khop": MODE_KHOP}[mode]
+    if centres is None:
+        centres = torch.arange(graph.num_nodes, dtype=torch.int32, device=dev)
+    centres = centres.to(device=dev, dtype=torch.int32).contiguous()
+    C = centres.numel()
+    i32 = dict(dtype=torch.int32, device=dev)
+    nv, ne = torch.zeros(max(C, 1), **i32), torch.zeros(max(C, 1), **i32)
+    step = int(max_centres) if max_centres else (4096 if large else 1 << 20)
+    cg = torch.empty(min(step, max(C, 1)), **i32)
+    status = torch.zeros(1, **i32)
+    with torch.cuda.device(dev):
+        st = _stream()
+        lwork, lbytes = None, 0
+        if large:
+            lbytes = int(lib.desco_partition_large_workspace_bytes(graph.max_graph_nodes, min(step, max(C, 1))))
+            lwork = torch.empty(lbytes, dtype=torch.uint8, device=dev)
+        for a in range(0, C, step):
+            n = min(step, C - a)
+            if large:
+                _lib.check(lib.desco_partition_large_count(
+                    _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres[a:]), n, depth,
+                    mode, graph.max_graph_nodes, _ptr(nv[a:]), _ptr(ne[a:]), _ptr(cg), _ptr(status), _ptr(lwork), lbytes, st),
+                    "desco_partition_large_count")
+            else:
+                _lib.check(lib.desco_partition_count(
+                    _ptr(graph.rowptr), _ptr(graph.col), _ptr(graph.graph_ptr), graph.num_graphs, _ptr(centres[a:]), n, depth,
+                    mode, graph.max_graph_nodes, _ptr(nv[a:]), _ptr(ne[a:]), _ptr(cg), _ptr(status), st), "desco_partition_count")
+        code = int(status.item())
+    if code != 0:
+        _lib.check(code, "partition kernel (device status)")
+    return nv[:C], ne[:C]
+
+
 _CAPACITY = {"rows_per_centre": 24.0, "edges_per_row": 6.0}  # running maxima of the batches seen so far
 
 

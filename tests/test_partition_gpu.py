@@ -205,6 +205,27 @@ def test_large_path_equals_bitset_path_full_sweep(cuda_device):
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("large", [False, True])
+def test_count_only_sizes_equal_packed_batch(cuda_device, large):
+    """partition_sizes (streaming count-only mode, chunked) = the row / edge counts of the packed neighborhoods; dropped
+    edge-free neighborhoods read (0, 0)."""
+    from desco_b200.data import DeviceCSR, partition_batch, partition_sizes
+    from desco_b200.graph import gen_powerlaw
+
+    csr = gen_powerlaw(6000, 24000, seed=11)
+    d = DeviceCSR.from_host(csr)
+    nv, ne = partition_sizes(d, None, 2, "hetero", large=large, max_centres=1000)
+    b = partition_batch(d, None, 2, "hetero", large=large)
+    nv, ne = nv.cpu().numpy(), ne.cpu().numpy()
+    got = b.to_numpy()
+    kept = got["indicator"]
+    want_nv, want_ne = np.zeros_like(nv), np.zeros_like(ne)
+    want_nv[kept] = np.diff(got["nbh_ptr"])
+    want_ne[kept] = np.diff(got["edge_ptr"][got["nbh_ptr"]])
+    assert np.array_equal(nv, want_nv) and np.array_equal(ne, want_ne)
+    assert int((nv == 0).sum()) == int((~kept).sum())
+
+
 def test_one_call_partition_grows_its_buffers(cuda_device):
     """desco_partition_batch reports ENOBUFS with the exact sizes when the caller's capacity is too small; the Python
     wrapper re-allocates once and the result is still bit-exact (here the capacity estimate is forced down to 1 row per
