@@ -303,6 +303,27 @@ def test_fused_path_tiny_and_mixed_neighborhoods(cuda_device):
     _check(om, pm, one)
 
 
+def test_fused_path_dense_and_full_tiles(cuda_device):
+    """Cliques: tiles whose edge count exceeds the staged capacity of the fused kernel (4096 edge records: the kernel then
+    reads the edges from global memory), neighborhoods of exactly 128 rows (one neighborhood = one full tile), canonical
+    rows of degree 127, and a batch where every row has the same (maximal) degree for the degree-ordered gather."""
+    import networkx as nx
+
+    from desco_b200.graph import csr_from_networkx
+    from oracle import partition as P
+
+    om, pm = _models(8)
+    gs = [nx.complete_graph(64), nx.complete_graph(60), nx.complete_graph(128), nx.complete_graph(70)]
+    gs += [nx.complete_bipartite_graph(50, 60), nx.path_graph(2), nx.star_graph(126)]
+    b = P.partition_dataset(csr_from_networkx(gs), 4)
+    assert np.diff(b["nbh_ptr"]).max() == 128
+    deg = np.diff(b["edge_ptr"])
+    tile_edges = np.add.reduceat(deg, b["nbh_ptr"][:-1])
+    assert tile_edges.max() > 4096  # a single neighborhood already overflows the staged edge records
+    for bs in (None, 512):
+        _check(om, pm, b, pyg_bs=bs, oracle64=True)
+
+
 def test_fused_path_reports_oversize_neighborhoods(cuda_device):
     """A neighborhood above 128 rows cannot be a fused tile: the Python surface routes the batch to the fp32 kernels,
     and the raw C ABI reports DESCO_ERANGE through the device status word instead of computing garbage silently."""
