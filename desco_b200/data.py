@@ -162,11 +162,46 @@ class NeighborhoodBatch:
         g1 = min(g1, self.num_neighborhoods)
         r0, r1 = (int(x) for x in self.nbh_ptr[[g0, g1]].cpu())
         e0, e1 = (int(x) for x in self.edge_ptr[[r0, r1]].cpu())
-        return NeighborhoodBatch(
+        out = NeighborhoodBatch(
             self.nbh_ptr[g0:g1 + 1] - r0, self.node_gid[r0:r1], self.edge_ptr[r0:r1 + 1] - e0, self.edge_col[e0:e1] - r0,
             self.edge_tri[e0:e1], self.centre[g0:g1], None, None, self.graph_ptr, g1 - g0, r1 - r0, e1 - e0,
             hetero=self.hetero, max_rows=self.max_rows,
         )
+        if "centre_last" in self._cache:
+            out._cache["centre_last"] = self._cache["centre_last"]
+        return out
+
+    def select(self, idx) -> "NeighborhoodBatch":
+        """The neighborhoods ``idx`` (any order, repeats allowed) gathered into their own packed batch - what one step of a
+        SHUFFLED DataLoader collates (``lightning_data.py:78-100`` with ``shuffle=True``).  Device-side gathers; the row and
+        edge totals are read on the host (one small sync)."""
+        dev = self.nbh_ptr.device
+        idx = torch.as_tensor(idx, device=dev).long().reshape(-1)
+        S = idx.numel()
+        ar = lambda n: torch.arange(n, device=dev)
+        ptr = self.nbh_ptr.long()
+        r0 = ptr[idx]
+        rows = ptr[idx + 1] - r0
+        new_ptr = torch.cat([rows.new_zeros(1), torch.cumsum(rows, 0)])
+        V2 = int(new_ptr[-1])
+        seg = torch.repeat_interleave(ar(S), rows, output_size=V2)       # selected neighborhood of each new row
+        old_row = r0[seg] + (ar(V2) - new_ptr[seg])
+        ep = self.edge_ptr.long()
+        e_first = ep[old_row]
+        deg = ep[old_row + 1] - e_first
+        new_eptr = torch.cat([deg.new_zeros(1), torch.cumsum(deg, 0)])
+        E2 = int(new_eptr[-1])
+        rseg = torch.repeat_interleave(ar(V2), deg, output_size=E2)       # new row of each new edge
+        old_e = e_first[rseg] + (ar(E2) - new_eptr[rseg])
+        shift = (new_ptr[:-1] - r0)[seg][rseg]                             # rows of a neighborhood move together
+        out = NeighborhoodBatch(
+            new_ptr.to(torch.int32), self.node_gid[old_row], new_eptr.to(torch.int32),
+            (self.edge_col[old_e].long() + shift).to(torch.int32), self.edge_tri[old_e], self.centre[idx], None, None,
+            self.graph_ptr, S, V2, E2, hetero=self.hetero, max_rows=self.max_rows,
+        )
+        if "centre_last" in self._cache:
+            out._cache["centre_last"] = self._cache["centre_last"]
+        return out
 
     @staticmethod
     def from_numpy(d: Dict[str, np.ndarray], device=None, hetero: bool = True) -> "NeighborhoodBatch":

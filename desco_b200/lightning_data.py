@@ -1,20 +1,25 @@
 """``subgraph_counting/lightning_data.py:59-100`` (``LightningDataLoader``): batches for the model entry points.
-pytorch_lightning / PyG loaders are optional here - the datasets of ``desco_b200.workload`` batch themselves."""
+
+The reference wraps PyG ``DataLoader``s (forked workers collating ``HeteroData``); here the datasets of
+``desco_b200.workload`` batch themselves on the device - consecutive chunks, or a fresh permutation per pass with
+``shuffle=True`` (``NeighborhoodBatch.select`` gathers the chunk into its own packed batch) - so ``num_workers`` is accepted
+and unused: the CUDA transform cannot run in forked workers.  pytorch_lightning is optional."""
 from __future__ import annotations
 
 
 class LightningDataLoader:
     def __init__(self, train_dataset=None, test_dataset=None, val_dataset=None, batch_size: int = 64,
-                 num_workers: int = 0, shuffle: bool = False):
-        if shuffle:
-            raise NotImplementedError("shuffle=True is a training option; the inference hot path iterates in order")
+                 num_workers: int = 0, shuffle: bool = False, generator=None):
         self.train_dataset, self.test_dataset, self.val_dataset = train_dataset, test_dataset, val_dataset
-        self.batch_size, self.num_workers, self.shuffle = batch_size, num_workers, shuffle  # workers: GPU path, unused
+        self.batch_size, self.num_workers, self.shuffle, self.generator = batch_size, num_workers, shuffle, generator
 
     def _loader(self, ds):
         if ds is None:
             raise ValueError("dataset not set")
-        return ds.loader(self.batch_size)
+        try:
+            return ds.loader(self.batch_size, shuffle=self.shuffle, generator=self.generator)
+        except TypeError:  # GossipDataset: one batch for the whole dataset, nothing to shuffle
+            return ds.loader(self.batch_size)
 
     def train_dataloader(self):
         return self._loader(self.train_dataset)

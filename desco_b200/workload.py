@@ -83,14 +83,33 @@ class NeighborhoodDataset:
     def __len__(self) -> int:
         return self.batch.num_neighborhoods
 
-    def loader(self, batch_size: int = 512) -> Iterator[NeighborhoodBatch]:
-        """Consecutive neighborhoods in chunks of ``batch_size`` (``config.py:255``) - the PyG ``DataLoader`` analogue."""
+    def loader(self, batch_size: int = 512, shuffle: bool = False, generator=None) -> Iterator[NeighborhoodBatch]:
+        """Neighborhoods in chunks of ``batch_size`` (``config.py:255``) - the PyG ``DataLoader`` analogue: consecutive, or
+        (``shuffle=True``) a fresh random permutation per pass, each chunk gathered into its own packed batch on the device.
+        The truth counts of the chunk ride along as ``batch.y`` once ``apply_truth_from_dataset`` has set them."""
         G = len(self)
+        y = getattr(self, "y", None)
+        if shuffle:
+            perm = torch.randperm(G, generator=generator, device="cpu").to(self.batch.nbh_ptr.device)
+            step = G if batch_size <= 0 else batch_size
+            for g0 in range(0, G, step):
+                idx = perm[g0:g0 + step]
+                b = self.batch.select(idx)
+                b.index_in_dataset = idx
+                if y is not None:
+                    b.y = y.to(idx.device)[idx]
+                yield b
+            return
         if batch_size <= 0 or batch_size >= G:
+            if y is not None:
+                self.batch.y = y
             yield self.batch
             return
         for g0 in range(0, G, batch_size):
-            yield self.batch.slice(g0, g0 + batch_size)
+            b = self.batch.slice(g0, g0 + batch_size)
+            if y is not None:
+                b.y = y[g0:g0 + batch_size]
+            yield b
 
     def apply_truth_from_dataset(self, truth: torch.Tensor):
         """``workload.py:296-301``: truth [#node, #query] -> y of the kept neighborhoods."""

@@ -52,6 +52,37 @@ def test_step_equals_eager_path_and_oracle(cuda_device, use_graph):
     assert ((counts.cpu() - want).abs() / want.abs().clamp(min=1.0)).max().item() <= 1e-4
 
 
+def test_bench_workload_matches_oracle(cuda_device):
+    """The exact workload bench.py times (BASELINE configs[1]: the first 4096 non-empty depth-4 neighborhoods of the
+    ENZYMES-shaped pool, 29 queries, collated 512 at a time) through the CUDA-graph step, ALL of it against the oracle:
+    partition + edge types bit-exact, counts within 1e-4 (bench.py itself re-checks a 1024-neighborhood slice per run)."""
+    import bench
+    from desco_b200.data import DeviceCSR
+    from desco_b200.pipeline import NeighborhoodCountStep
+    from oracle import model as M
+    from oracle import partition as P
+
+    om, pm = _model(0)
+    csr, centres = bench.build_workload(0)
+    assert len(centres) == bench.NUM_NBH == 4096
+    g = DeviceCSR.from_host(csr)
+    ct = torch.as_tensor(centres, dtype=torch.int32, device="cuda")
+    step = NeighborhoodCountStep(pm, g, ct, depth=bench.DEPTH)
+    step(ct)
+    counts, kept = step.result()
+    ref = P.partition_dataset(csr, bench.DEPTH, centres=centres)
+    G, V, E = len(ref["centre"]), int(ref["nbh_ptr"][-1]), int(ref["edge_ptr"][-1])
+    assert G == 4096 and np.array_equal(kept.cpu().numpy(), ref["centre"])
+    assert np.array_equal(step.nbh_ptr[: G + 1].cpu().numpy(), ref["nbh_ptr"])
+    assert np.array_equal(step.node_gid[:V].cpu().numpy(), ref["node_gid"])
+    assert np.array_equal(step.edge_col[:E].cpu().numpy(), ref["edge_col"])
+    assert np.array_equal(step.edge_tri[:E].cpu().numpy(), ref["edge_tri"])
+    with torch.no_grad():
+        want = om.graph_to_count(ref, M.query_batch(), pyg_batch_size=512)
+    assert counts.shape == (4096, 29)
+    assert ((counts.cpu() - want).abs() / want.abs().clamp(min=1.0)).max().item() <= 1e-4
+
+
 def test_step_reports_capacity_overflow_and_unsupported_batches(cuda_device):
     from desco_b200 import _lib
     from desco_b200.data import DeviceCSR

@@ -79,6 +79,47 @@ def test_loader_batches_equal_whole_dataset(cuda_device):
     assert (parts - whole).abs().max().item() <= 1e-6
 
 
+def test_shuffled_loader_and_select(cuda_device):
+    """LightningDataLoader(shuffle=True) (lightning_data.py:59-100): every neighborhood exactly once per pass, in a fresh
+    seeded permutation; a gathered chunk (NeighborhoodBatch.select) is the same packed structure a contiguous slice gives
+    and counts to the same values as the rows of the one-pass batch; the truth counts ride along as batch.y."""
+    from desco_b200.lightning_data import LightningDataLoader
+    from desco_b200.workload import Workload
+
+    _, _, pm, _ = _models(4)
+    wl = Workload(gen_mutag_shaped(seed=2, num_graphs=60), None)
+    wl.generate_pipeline_datasets(depth_neigh=4)
+    nd = wl.neighborhood_dataset
+    G = len(nd)
+    nd.y = torch.arange(G * 3, dtype=torch.float32, device="cuda").reshape(G, 3)
+    pm.set_pyg_batch_size(-1)  # the reference quirk depends on the collated order: off for an order-free comparison
+    with torch.no_grad():
+        whole = pm.graph_to_count(nd.batch)
+    # select on a contiguous range == slice
+    a, b = nd.batch.slice(100, 300).to_numpy(), nd.batch.select(torch.arange(100, 300)).to_numpy()
+    for k in ("nbh_ptr", "node_gid", "edge_ptr", "edge_col", "edge_tri", "centre"):
+        assert np.array_equal(a[k], b[k]), k
+    gen = torch.Generator().manual_seed(7)
+    dl = LightningDataLoader(train_dataset=nd, batch_size=256, shuffle=True, generator=gen)
+    seen, passes = [], []
+    for _ in range(2):
+        order = []
+        for bt in dl.train_dataloader():
+            idx = bt.index_in_dataset
+            assert torch.equal(bt.y, nd.y[idx]) and torch.equal(bt.centre, nd.batch.centre[idx])
+            with torch.no_grad():
+                got = pm.graph_to_count(bt)
+            assert _rel(got, whole[idx]) <= 1e-5
+            order.append(idx)
+        order = torch.cat(order)
+        assert torch.equal(torch.sort(order).values, torch.arange(G, device=order.device))
+        passes.append(order)
+    assert not torch.equal(passes[0], passes[1]) and not torch.equal(passes[0], torch.arange(G, device="cuda"))
+    # in-order loader hands out y as well
+    ys = torch.cat([bt.y for bt in LightningDataLoader(test_dataset=nd, batch_size=256).test_dataloader()])
+    assert torch.equal(ys, nd.y)
+
+
 def test_sharded_pipeline_single_rank_equals_direct(cuda_device):
     """distributed.ShardedPipeline with world size 1 (no process group): same numbers as the direct calls, and the
     node-range gossip entry with several ranges stitched by hand equals the single call."""
