@@ -6,12 +6,14 @@
 //                             pred[g,q] = w2 . leaky_.01( t_g . W1a + (q_q . W1b + b1) ) + b2 ;  count = 2^pred - 1
 //
 // The reference runs these as 4 + 29 x 2 cuBLAS launches on [G, .] activations that round-trip through HBM; here a CTA
-// owns 32 neighborhoods and keeps every intermediate in shared memory.  These GEMMs are tiny per row (90 k MAC) and the
-// sums cancel heavily, so they run as exact fp32 FFMA on all SMs (G = 4096 -> 128 CTAs) instead of a 6-pass bf16 split
-// on a 128-row tensor-core tile (32 CTAs).  Two warp-level GEMM shapes:
-//   * N = 64  : split-K - each of the 8 warps multiplies its K-slice into a full 32 x 64 partial (8 x 8 outputs per
+// owns 16 neighborhoods and keeps every intermediate in shared memory (two CTAs per SM: the weights stream from L2 with
+// no explicit prefetch, so a second CTA is what hides their latency).  These GEMMs are tiny per row (90 k MAC) and the
+// sums cancel heavily, so they run as exact fp32 FFMA on all SMs (G = 4096 -> 256 CTAs) instead of a 6-pass bf16 split
+// on a 128-row tensor-core tile (32 CTAs).  The query half of the head's first Linear (q_q . W1b + b1, the same for every
+// neighborhood) is computed once per call by count_head_query_kernel.  Two warp-level GEMM shapes:
+//   * N = 64  : split-K - each of the 8 warps multiplies its K-slice into a full 16 x 64 partial (4 x 8 outputs per
 //               lane, weights straight from L1/L2 as float4), partials are summed through shared memory;
-//   * N = 256 : split-N - each warp owns 32 output columns over the whole K = 64 (8 x 4 outputs per lane).
+//   * N = 256 : split-N - each warp owns 32 output columns over the whole K = 64 (4 x 4 outputs per lane).
 #include "common.cuh"
 #include "shmp_internal.h"
 #include "../../include/desco_b200.h"
@@ -19,7 +21,8 @@
 namespace {
 
 constexpr int F = 64;
-constexpr int ROWS = 32;       // neighborhoods per CTA
+constexpr int ROWS = 16;       // neighborhoods per CTA (16: ~95 KB of shared memory -> two CTAs per SM hide the weight loads of each other)
+constexpr int RI = ROWS / 4;   // rows per lane: ry + 4 i
 constexpr int THREADS = 256;
 constexpr int NW = THREADS / 32;
 constexpr int H4 = 4 * F;      // 256
@@ -40,23 +43,24 @@ template <int LDX>
 __device__ __forceinline__ void splitk_gemm64(const float* sX, int K, const float* __restrict__ W, float* sPart, int warp,
                                               int lane) {
   const int ry = lane >> 3, cx = lane & 7;
-  float acc[8][8];
+  float acc[RI][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RI; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const int kper = K / NW;
   const int k0 = warp * kper;
+#pragma unroll 2
   for (int k4 = k0; k4 < k0 + kper; k4 += 4) {
-    float4 a[8];
+    float4 a[RI];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(sX + (ry + 4 * i) * LDX + k4);
+    for (int i = 0; i < RI; ++i) a[i] = *reinterpret_cast<const float4*>(sX + (ry + 4 * i) * LDX + k4);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k4 + kk) * F + 8 * cx));
       const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k4 + kk) * F + 8 * cx + 4));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < RI; ++i) {
         const float av = comp(a[i], kk);
         acc[i][0] = fmaf(av, w0.x, acc[i][0]); acc[i][1] = fmaf(av, w0.y, acc[i][1]);
         acc[i][2] = fmaf(av, w0.z, acc[i][2]); acc[i][3] = fmaf(av, w0.w, acc[i][3]);
@@ -66,7 +70,7 @@ __device__ __forceinline__ void splitk_gemm64(const float* sX, int K, const floa
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < RI; ++i) {
     float* dst = sPart + ((size_t)warp * ROWS + ry + 4 * i) * F + 8 * cx;
     *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
@@ -96,21 +100,21 @@ __device__ __forceinline__ void splitn_gemm256(const float* sX, const float* __r
                                                int act, float slope, float* sY, int warp, int lane) {
   const int ry = lane >> 3, cx = lane & 7;
   const int c0 = 32 * warp + 4 * cx;
-  float acc[8][4];
+  float acc[RI][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 2
   for (int k4 = 0; k4 < F; k4 += 4) {
-    float4 a[8];
+    float4 a[RI];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(sX + (ry + 4 * i) * LDX + k4);
+    for (int i = 0; i < RI; ++i) a[i] = *reinterpret_cast<const float4*>(sX + (ry + 4 * i) * LDX + k4);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k4 + kk) * H4 + c0));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < RI; ++i) {
         const float av = comp(a[i], kk);
         acc[i][0] = fmaf(av, w.x, acc[i][0]); acc[i][1] = fmaf(av, w.y, acc[i][1]);
         acc[i][2] = fmaf(av, w.z, acc[i][2]); acc[i][3] = fmaf(av, w.w, acc[i][3]);
@@ -120,7 +124,7 @@ __device__ __forceinline__ void splitn_gemm256(const float* sX, const float* __r
   float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
   if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + c0));
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < RI; ++i) {
     float4 o;
     o.x = act_fn(acc[i][0] + b.x, act, slope); o.y = act_fn(acc[i][1] + b.y, act, slope);
     o.z = act_fn(acc[i][2] + b.z, act, slope); o.w = act_fn(acc[i][3] + b.w, act, slope);
@@ -138,7 +142,7 @@ struct ChainArgs {
   const int32_t* g_dev;                          // device-resident G (stream-ordered form) or NULL
 };
 
-__global__ void __launch_bounds__(THREADS, 1) readout_chain_kernel(const ChainArgs p) {
+__global__ void __launch_bounds__(THREADS, 2) readout_chain_kernel(const ChainArgs p) {
   extern __shared__ __align__(16) float sm[];
   const int ldx = p.K0 + 4;                      // K0 % 32 == 0 -> ldx = 4 mod 32
   float* sX = sm;                                // [ROWS][ldx]
@@ -162,23 +166,24 @@ __global__ void __launch_bounds__(THREADS, 1) readout_chain_kernel(const ChainAr
   // Linear(K0,64): split-K like splitk_gemm64, written out because the row pitch of sX is a run-time value
   {
     const int ry = lane >> 3, cx = lane & 7;
-    float acc[8][8];
+    float acc[RI][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RI; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     const int kper = p.K0 / NW;  // K0 % 32 == 0
     const int k0 = warp * kper;
+#pragma unroll 2
     for (int k4 = k0; k4 < k0 + kper; k4 += 4) {
-      float4 a[8];
+      float4 a[RI];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(sX + (ry + 4 * i) * ldx + k4);
+      for (int i = 0; i < RI; ++i) a[i] = *reinterpret_cast<const float4*>(sX + (ry + 4 * i) * ldx + k4);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.P0 + (size_t)(k4 + kk) * F + 8 * cx));
         const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.P0 + (size_t)(k4 + kk) * F + 8 * cx + 4));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < RI; ++i) {
           const float av = comp(a[i], kk);
           acc[i][0] = fmaf(av, w0.x, acc[i][0]); acc[i][1] = fmaf(av, w0.y, acc[i][1]);
           acc[i][2] = fmaf(av, w0.z, acc[i][2]); acc[i][3] = fmaf(av, w0.w, acc[i][3]);
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1) readout_chain_kernel(const ChainAr
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < RI; ++i) {
       float* dst = sPart + ((size_t)warp * ROWS + ry + 4 * i) * F + 8 * cx;
       *reinterpret_cast<float4*>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
@@ -213,36 +218,53 @@ __global__ void __launch_bounds__(THREADS, 1) readout_chain_kernel(const ChainAr
 // ------------------------------------------------------------------------------------------------------------------
 struct HeadArgs {
   const float* emb_t; int G;    // [G][64]
-  const float* emb_q; int Q;    // [Q][64], Q <= 32
-  const float *W1a, *W1b, *b1, *w2, *b2;  // [64][256], [64][256], [256], [256], [1]
+  const float* Bq; int Q;       // [Q][256] = q_q . W1b + b1 (count_head_query_kernel), Q <= 32
+  const float *W1a, *w2, *b2;   // [64][256], [256], [1]
   float* pred;                  // [G][Q] or NULL
   float* count;                 // [G][Q] or NULL
   const int32_t* g_dev;         // device-resident G (stream-ordered form) or NULL
 };
+constexpr int QROWS = 32;       // query rows held in shared memory
 
-__global__ void __launch_bounds__(THREADS, 1) count_head_fused_kernel(const HeadArgs p) {
+// Bq[q][0..256) = emb_q[q] . W1b + b1: the query half of the head's first Linear, once per call instead of once per CTA
+__global__ void __launch_bounds__(H4) count_head_query_kernel(const float* __restrict__ emb_q, const float* __restrict__ W1b,
+                                                              const float* __restrict__ b1, float* __restrict__ Bq) {
+  __shared__ float sq[F];
+  const int q = blockIdx.x, j = threadIdx.x;
+  if (j < F) sq[j] = emb_q[(size_t)q * F + j];
+  __syncthreads();
+  float w[F];  // all 64 loads in flight before the first FMA (the kernel is one L2 round trip long)
+#pragma unroll
+  for (int k = 0; k < F; ++k) w[k] = __ldg(W1b + (size_t)k * H4 + j);
+  float acc = __ldg(b1 + j);
+#pragma unroll
+  for (int k = 0; k < F; ++k) acc = fmaf(sq[k], w[k], acc);
+  Bq[(size_t)q * H4 + j] = acc;
+}
+
+__global__ void __launch_bounds__(THREADS, 2) count_head_fused_kernel(const HeadArgs p) {
   extern __shared__ __align__(16) float sm[];
-  float* sE = sm;                      // [ROWS][LD64]  target embeddings
-  float* sQ = sE + ROWS * LD64;        // [ROWS][LD64]  query embeddings (rows >= Q are zero)
-  float* sT = sQ + ROWS * LD64;        // [ROWS][LD256] t_g . W1a
-  float* sB = sT + ROWS * LD256;       // [ROWS][LD256] q_q . W1b + b1
-  float* sW2 = sB + ROWS * LD256;      // [256]
+  float* sE = sm;                      // [ROWS][LD64]   target embeddings
+  float* sT = sE + ROWS * LD64;        // [ROWS][LD256]  t_g . W1a
+  float* sB = sT + ROWS * LD256;       // [QROWS][LD256] q_q . W1b + b1
+  float* sW2 = sB + QROWS * LD256;     // [256]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g0 = blockIdx.x * ROWS;
   const int G = p.g_dev ? min(p.G, *p.g_dev) : p.G;
   if (g0 >= G) return;
   for (int i = tid; i < ROWS * (F / 4); i += THREADS) {
     const int r = i >> 4, c4 = (i & 15) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), q = v;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g0 + r < G) v = __ldg(reinterpret_cast<const float4*>(p.emb_t + (size_t)(g0 + r) * F + c4));
-    if (r < p.Q) q = __ldg(reinterpret_cast<const float4*>(p.emb_q + (size_t)r * F + c4));
     *reinterpret_cast<float4*>(sE + r * LD64 + c4) = v;
-    *reinterpret_cast<float4*>(sQ + r * LD64 + c4) = q;
+  }
+  for (int i = tid; i < p.Q * (H4 / 4); i += THREADS) {
+    const int r = i >> 6, c4 = (i & 63) * 4;
+    *reinterpret_cast<float4*>(sB + r * LD256 + c4) = __ldg(reinterpret_cast<const float4*>(p.Bq + (size_t)r * H4 + c4));
   }
   for (int i = tid; i < H4; i += THREADS) sW2[i] = __ldg(p.w2 + i);
   __syncthreads();
   splitn_gemm256<LD64, LD256>(sE, p.W1a, nullptr, ACT_NONE, 0.f, sT, warp, lane);
-  splitn_gemm256<LD64, LD256>(sQ, p.W1b, p.b1, ACT_NONE, 0.f, sB, warp, lane);
   __syncthreads();
   const float bias2 = __ldg(p.b2);
   const int pairs = ROWS * p.Q;
@@ -296,19 +318,21 @@ int desco_internal_readout_chain(const float* Z, int ldz, int K0, int G, const f
 
 int desco_internal_count_head_fused(const float* emb_t, int G, const float* emb_q, int Q, const float* W1a, const float* W1b,
                                     const float* b1, const float* w2, const float* b2, float* pred, float* count,
-                                    const int32_t* g_dev, cudaStream_t s) {
+                                    float* Bq, const int32_t* g_dev, cudaStream_t s) {
   if (G == 0 || Q == 0) return DESCO_OK;
-  if (Q > ROWS) return DESCO_ERANGE;
-  const size_t smem = ((size_t)2 * ROWS * LD64 + 2 * ROWS * LD256 + H4) * sizeof(float);
+  if (Q > QROWS) return DESCO_ERANGE;
+  if (!Bq) return DESCO_EINVAL;
+  const size_t smem = ((size_t)ROWS * LD64 + ROWS * LD256 + QROWS * LD256 + H4) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     DESCO_CUDA_TRY(cudaFuncSetAttribute(count_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   HeadArgs a;
-  a.emb_t = emb_t; a.G = G; a.emb_q = emb_q; a.Q = Q;
-  a.W1a = W1a; a.W1b = W1b; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.pred = pred; a.count = count; a.g_dev = g_dev;
-  DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s);
+  a.emb_t = emb_t; a.G = G; a.Bq = Bq; a.Q = Q;
+  a.W1a = W1a; a.w2 = w2; a.b2 = b2; a.pred = pred; a.count = count; a.g_dev = g_dev;
+  DescoProfScope prof(DESCO_PROF_SHMP_OTHER, s, 2);
+  count_head_query_kernel<<<Q, H4, 0, s>>>(emb_q, W1b, b1, Bq);
   count_head_fused_kernel<<<(G + ROWS - 1) / ROWS, THREADS, smem, s>>>(a);
   DESCO_LAUNCH_CHECK();
   return DESCO_OK;

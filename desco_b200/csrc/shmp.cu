@@ -645,7 +645,7 @@ static int count_head_impl(const float* emb_target, int32_t num_neighborhoods, c
   const float* w2 = b1 + HEAD_H;
   const float* b2 = w2 + HEAD_H;
   if (Q <= 32)  // one fused launch (csrc/readout.cu); the multi-launch path below serves larger query sets
-    return desco_internal_count_head_fused(emb_target, G, emb_query, Q, W1a, W1b, b1, w2, b2, out_pred, out_count, g_dev, s);
+    return desco_internal_count_head_fused(emb_target, G, emb_query, Q, W1a, W1b, b1, w2, b2, out_pred, out_count, Bq, g_dev, s);
   int rc;
   if (precision != DESCO_PRECISION_FP32) {
     if (!w_head_tc || !status) return DESCO_EINVAL;

@@ -36,9 +36,10 @@ int desco_internal_readout_chain(const float* Z, int ldz, int K0, int G, const f
                                  float* out, const int32_t* g_dev, cudaStream_t s);
 
 // Factorised count head for Q <= 32 queries in one launch, fp32 (csrc/readout.cu); DESCO_ERANGE for larger Q.
+// Bq: [Q][256] scratch for the query half of the first Linear (q . W1b + b1, computed once per call by a small launch)
 int desco_internal_count_head_fused(const float* emb_t, int G, const float* emb_q, int Q, const float* W1a, const float* W1b,
                                     const float* b1, const float* w2, const float* b2, float* pred, float* count,
-                                    const int32_t* g_dev, cudaStream_t s);
+                                    float* Bq, const int32_t* g_dev, cudaStream_t s);
 
 /* bytes of one layer in the multi-tile weight blob (csrc/shmp_mt.cu): 3 K blocks x [hi | lo] images of a [64 n x 64 k]
  * block of Wc^T (tcpack.pack_b_operand) */
