@@ -396,16 +396,7 @@ __global__ void __launch_bounds__(THREADS, 2) gossip_layer1_kernel(
 // The staging buffer is walked in chunks of tiles, so its size is bounded whatever the graph.
 // ------------------------------------------------------------------------------------------------------------------
 namespace gtc {
-// packed fp32x2 arithmetic (one issue slot for two lanes of the same operation; IEEE rounding as the scalar forms)
-__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
+// packed fp32x2 add (one issue slot for two lanes; IEEE rounding as the scalar form)
 __device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
   float2 d;
   asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
@@ -422,18 +413,88 @@ constexpr int TILE_BYTES = 2 * SLOT + TILE_CD;   // staging per tile: u slot | x
 constexpr int HUB_DEG = 512;                     // rows with more neighbours are gathered by the whole CTA
 
 // ---------------------------------------------------------------- gather ----------------------------------------
-constexpr int G_THREADS = 256;
+// u_i = g1 * sum_{j<i} x1_j + (1-g1) * sum_{j>i} x1_j with x1_j = relu(a_j . W), a_j = (dmix_j, smix_j, c_j, 1) and W the
+// 4 x 64 matrix [alpha_q; beta; delta; gamma_q].  Both gates are positive, so the gate goes inside the relu:
+// u_i = sum_j relu((w_j a_j) . W), w_j = g1 or 1-g1 - ONE sum, no j<i / j>i split.  The 4-deep dot products run on the
+// warp-level tensor path (mma.sync m16n8k8, tf32; M = 16 features, N = 8 neighbour records): the K = 8 slots hold the
+// tf32 hi and lo parts of the weights, the scalars are applied as their hi part and then their lo part, so all four
+// partial products are formed and accumulated in fp32 (operands carry 20+ bits: 1e-6 relative, inside the 1e-4 budget).
+// What is left on the CUDA cores is relu + add.
+//
+// The eight columns of an MMA block belong to EIGHT DIFFERENT ROWS (an "octet"; one neighbour of each per block): lane
+// (g, t) of the fragment layout brings scalar t of the next neighbour of row g - no shuffles to build the operand - and
+// the accumulator columns 2t, 2t+1 it receives are the running sums of rows 2t, 2t+1 - no reduction across lanes, and
+// every per-row cost (own record, operand-image stores) is paid once per eight rows.  The rows of the tile are
+// counting-sorted by degree so that the rows of an octet are equally long; a row beyond OCT_DEG neighbours is walked by
+// a warp alone as eight interleaved sub-rows (sums folded at the end), a row beyond HUB_DEG by the whole CTA.
+//
+// The sweep is bound by the latency of the dependent col[] -> S4[] loads, so a warp brings a whole SLAB (8 sub-rows x
+// up to OCT_DEG neighbours) at once: the adjacency entries with one load per lane and step, then every neighbour's
+// 16-byte record with cp.async straight into the warp's shared-memory slab - up to 264 records in flight per warp with
+// no register held - and only then runs the tensor-core blocks out of shared memory.
+// A row's sum depends only on its own degree class, never on the tile it sits in (sharded == unsharded, bit for bit).
+constexpr int G_THREADS = 128;
 constexpr int G_NW = G_THREADS / 32;
-constexpr int GR = 1;  // rows whose loads are in flight together (more = more code: the kernel is I-cache sensitive)
+constexpr int OCT_DEG = 32;             // neighbours per sub-row of a slab
+constexpr int G_NBUCKET = OCT_DEG + 3;  // hub | wide | degree OCT_DEG ... 0
+constexpr int VB_LD = 140;              // floats per sub-row: OCT_DEG records + the row's own + pad (140 mod 32 = 12: the
+                                        // 32 lanes of a block read 32 different banks)
+constexpr int JB_LD = OCT_DEG + 1;
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// d = A(16x8, row) . B(8x8, col) + c.  bb holds the lane's B fragment as a register pair: both K halves carry the same
+// value (K slots 0-3 meet the hi parts of the weights, slots 4-7 their lo parts); passing the pair as one 64-bit operand
+// lets the four MMAs of a block share it (two 32-bit operands made ptxas rebuild the pair before every MMA).
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint64_t bb, const float (&c)[4]) {
+  asm volatile(
+      "{\n\t.reg .b32 b0, b1;\n\tmov.b64 {b0, b1}, %8;\n\t"
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {b0,b1}, {%9,%10,%11,%12};\n\t}"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "l"(bb), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+__device__ __forceinline__ uint64_t dup64(uint32_t x) {
+  uint64_t r;
+  asm volatile("mov.b64 %0, {%1, %1};" : "=l"(r) : "r"(x));  // volatile: one pair per block, never rematerialised per MMA
+  return r;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc05::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// 8 consecutive fp32 -> one 16-byte chunk of bf16 hi and one of lo
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 f = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
 __global__ void __launch_bounds__(G_THREADS, 5) gossip_gather_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int node_begin, int node_end,
     const float4* __restrict__ S4, int Q, int q_begin, const float* __restrict__ qvec, const float* __restrict__ wg,
     long long tile0, uint8_t* __restrict__ stage) {
-  __shared__ float4 s_slot[G_NW * 32];  // per-warp staging of 32 neighbours / per-warp partial sums of a hub row
-  __shared__ uint8_t s_hubs[TR];
-  __shared__ int s_nhub, s_next;
+  __shared__ __align__(16) float s_vb[G_NW][8][VB_LD];  // per warp: the slab's records [sub-row][neighbour][4 scalars]
+  __shared__ int s_jb[G_NW][8][JB_LD];                  // ... and their node ids
+  __shared__ float4 s_part[G_NW][8][2];                 // hub rows: per-warp partial sums, [g][8 features]
+  __shared__ int s_eb[TR], s_dg[TR];                    // first adjacency entry and degree of the tile's rows
+  __shared__ int s_hist[G_NBUCKET + 1];
+  __shared__ uint8_t s_order[TR];                       // tile rows in descending degree order
+  __shared__ int s_next, s_nhub, s_nwide;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;  // mma fragment coordinates = (sub-row, scalar / entry phase) of the loader
   const long long tile = tile0 + blockIdx.x;
   const int q = (int)(tile % Q);
   const int i0 = node_begin + (int)(tile / Q) * TR;
@@ -442,163 +503,203 @@ __global__ void __launch_bounds__(G_THREADS, 5) gossip_gather_kernel(
   float* g_c = reinterpret_cast<float*>(gA1 + SLOT);
   float* g_d1 = g_c + TR;
   const float* qv = qvec + (size_t)(q_begin + q) * QV;
-  const float g1 = qv[3 * F + 1];
-  const float2 alpha = *reinterpret_cast<const float2*>(qv + 2 * lane);
-  const float2 gamma = *reinterpret_cast<const float2*>(qv + F + 2 * lane);
-  const float2 beta = *reinterpret_cast<const float2*>(wg + WG_BETA + 2 * lane);
-  const float2 delta = *reinterpret_cast<const float2*>(wg + WG_DELTA + 2 * lane);
-  auto x1_of = [&](const float4 s) {
-    float2 r;
-    r.x = fmaxf(fmaf(s.x, alpha.x, fmaf(s.y, beta.x, fmaf(s.z, delta.x, gamma.x))), 0.f);
-    r.y = fmaxf(fmaf(s.x, alpha.y, fmaf(s.y, beta.y, fmaf(s.z, delta.y, gamma.y))), 0.f);
-    return r;
-  };
-  // 32 adjacency entries of a row starting at `base`, in two steps so that the loads of several rows are in flight
-  // together: fetch = every lane loads one neighbour's scalars; consume = the lanes park them in the warp's slot and all
-  // walk it (one broadcast 16-byte shared load per neighbour), recomputing their two features of x1_j.  The row is
-  // sorted, so the j < i neighbours are a prefix: no per-edge compare.
-  struct Fetch { int j; float4 s; int n; };
-  auto fetch = [&](int base, int ee) {
-    Fetch f;
-    const int e = base + lane;
-    f.j = 0x7fffffff;
-    f.s = make_float4(0.f, 0.f, 0.f, 0.f);
-    f.n = max(0, min(32, ee - base));
-    if (e < ee) {
-      f.j = col[e];
-      f.s = S4[(size_t)f.j * Q + q];
-    }
-    return f;
-  };
-  // Packed form of x1_of for TWO neighbours at a time (sm_100 fp32x2 pipe: half the issue slots; the gather is issue
-  // bound): the warp's slot holds the neighbours' scalars as three arrays, so one broadcast 8-byte load brings the pair
-  // (x_k, x_k+1), and the lane's coefficients are kept as duplicated pairs.  Same operations in the same order per
-  // element as x1_of, and the same even / odd accumulation as before: results are bit-identical.
-  const float2 aX = make_float2(alpha.x, alpha.x), aY = make_float2(alpha.y, alpha.y);
-  const float2 bX = make_float2(beta.x, beta.x), bY = make_float2(beta.y, beta.y);
-  const float2 dX = make_float2(delta.x, delta.x), dY = make_float2(delta.y, delta.y);
-  const float2 gX = make_float2(gamma.x, gamma.x), gY = make_float2(gamma.y, gamma.y);
-  auto consume = [&](const Fetch& f, int i, float2& lt, float2& gt) {
-    float* sl = reinterpret_cast<float*>(s_slot) + warp * 128;  // x[0..34) | y at +40 | z at +80 (8-byte aligned starts)
-    const int n = f.n;
-    const int nlt = __popc(__ballot_sync(FULL_MASK, f.j < i));
-    const int pos = lane + ((lane >= nlt) ? (nlt & 1) : 0);  // the j > i run starts on an even slot too
-    sl[pos] = f.s.x; sl[40 + pos] = f.s.y; sl[80 + pos] = f.s.z;
-    __syncwarp();
-    auto run = [&](int k0, int k1, float2& acc) {  // neighbours in slots [k0, k1), k0 even
-      float2 ex = make_float2(0.f, 0.f), ey = ex;  // feature x / y of this lane, (even, odd) neighbours
-      int k = k0;
-#pragma unroll 2
-      for (; k + 1 < k1; k += 2) {
-        const float2 X = *reinterpret_cast<const float2*>(sl + k), Y = *reinterpret_cast<const float2*>(sl + 40 + k),
-                     Z = *reinterpret_cast<const float2*>(sl + 80 + k);
-        float2 vx = fma2(X, aX, fma2(Y, bX, fma2(Z, dX, gX)));
-        float2 vy = fma2(X, aY, fma2(Y, bY, fma2(Z, dY, gY)));
-        vx.x = fmaxf(vx.x, 0.f); vx.y = fmaxf(vx.y, 0.f); vy.x = fmaxf(vy.x, 0.f); vy.y = fmaxf(vy.y, 0.f);
-        ex = add2(ex, vx);
-        ey = add2(ey, vy);
-      }
-      if (k < k1) {
-        const float2 v = x1_of(make_float4(sl[k], sl[40 + k], sl[80 + k], 0.f));
-        ex.x += v.x; ey.x += v.y;
-      }
-      acc.x += ex.x + ex.y;
-      acc.y += ey.x + ey.y;
-    };
-    run(0, nlt, lt);
-    const int g0 = nlt + (nlt & 1);
-    run(g0, g0 + (n - nlt), gt);
-    __syncwarp();
-  };
-  auto store_row = [&](uint8_t* img, int r, float2 v) {  // two features of row r as bf16 hi / lo, swizzled
-    const uint32_t off = tc05::sw128_offset(r, 2 * lane);
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
-    const float2 f = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v.x - f.x, v.y - f.y);
-    *reinterpret_cast<__nv_bfloat162*>(img + off) = h;
-    *reinterpret_cast<__nv_bfloat162*>(img + TR * 128 + off) = l;
-  };
-  if (tid == 0) { s_nhub = 0; s_next = G_NW; }
-  __syncthreads();
+  const float g1 = qv[3 * F + 1], g1c = 1.f - g1;
+  const char* Srec = reinterpret_cast<const char*>(S4) + q * 16;  // record of query q of node 0
+  const uint32_t rec_bytes = (uint32_t)Q * 16u;                   // one node's records of the group
+  float* vrow = s_vb[warp][g];
+  int* jrow = s_jb[warp][g];
 
-  // ---- x1_i and u_i = g1 * sum_{j<i} x1_j + (1-g1) * sum_{j>i} x1_j; one warp per row, hub rows deferred.  Rows are
-  // dealt by a ticket: degrees are power-law distributed, and with a static stride the warp that met the long rows kept
-  // the other seven waiting at the barrier below (22 % of the stall samples) ----
-  static_assert(GR == 1, "the row ticket hands out one row at a time");
-#pragma unroll 1
-  for (int r0 = warp; r0 < TR;) {
-    int eb[GR], ee[GR];
-    bool hub[GR];
-    Fetch f[GR];
-#pragma unroll
-    for (int k = 0; k < GR; ++k) {
-      const int i = i0 + r0 + G_NW * k;
-      eb[k] = ee[k] = 0;
-      if (i < node_end) { eb[k] = rowptr[i]; ee[k] = rowptr[i + 1]; }
-    }
-#pragma unroll
-    for (int k = 0; k < GR; ++k) {
-      hub[k] = ee[k] - eb[k] > HUB_DEG;
-      if (hub[k]) {
-        if (lane == 0) s_hubs[atomicAdd(&s_nhub, 1)] = (uint8_t)(r0 + G_NW * k);
-        ee[k] = eb[k];
-      }
-      f[k] = fetch(eb[k], ee[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < GR; ++k) {
-      const int r = r0 + G_NW * k, i = i0 + r;
-      float2 u = make_float2(0.f, 0.f), x1 = u;
-      float c = 0.f, d1 = 0.f;
-      if (i < node_end) {
-        const float4 own = S4[(size_t)i * Q + q];
-        x1 = x1_of(own);
-        c = own.z;
-        d1 = own.w;
-        float2 lt = make_float2(0.f, 0.f), gt = lt;
-        Fetch cur = f[k];
-#pragma unroll 1
-        for (int base = eb[k] + 32; base < ee[k]; base += 32) {  // longer rows: the next 32 entries load under this batch
-          const Fetch nxt = fetch(base, ee[k]);
-          consume(cur, i, lt, gt);
-          cur = nxt;
-        }
-        consume(cur, i, lt, gt);
-        u.x = g1 * lt.x + (1.f - g1) * gt.x;
-        u.y = g1 * lt.y + (1.f - g1) * gt.y;
-      }
-      if (!hub[k]) store_row(gA0, r, u);
-      store_row(gA1, r, x1);
-      if (lane == 0) {
-        g_c[r] = c;
-        g_d1[r] = d1;
-      }
-    }
-    if (lane == 0) r0 = atomicAdd(&s_next, 1);
-    r0 = __shfl_sync(FULL_MASK, r0, 0);
+  // ---- tile set-up: row extents into shared memory, counting sort of the rows by degree class ----
+  if (tid <= G_NBUCKET) s_hist[tid] = 0;
+  if (tid == 0) s_next = G_NW;
+  __syncthreads();
+  int bucket = 0, slot = 0;
+  if (tid < TR) {
+    const int i = i0 + tid;
+    int eb = 0, deg = 0;
+    if (i < node_end) { eb = __ldg(rowptr + i); deg = __ldg(rowptr + i + 1) - eb; }
+    s_eb[tid] = eb;
+    s_dg[tid] = deg;
+    bucket = deg > HUB_DEG ? 0 : deg > OCT_DEG ? 1 : 2 + OCT_DEG - deg;
+    slot = atomicAdd(&s_hist[bucket], 1);
   }
   __syncthreads();
-  // ---- hub rows: 32-edge chunks dealt over all warps of the CTA, partial sums added in warp order ----
-  for (int h = 0, nh = s_nhub; h < nh; ++h) {
-    const int r = s_hubs[h], i = i0 + r;
-    const int eb = rowptr[i], ee = rowptr[i + 1];
-    float2 lt = make_float2(0.f, 0.f), gt = lt;
-    for (int base = eb + 32 * warp; base < ee; base += 32 * G_NW * GR) {
-      Fetch f[GR];
+  if (warp == 0) {  // exclusive scan of the bucket counts, two buckets per lane
+    static_assert(G_NBUCKET <= 64, "two buckets per lane");
+    int cnt[2], sum = 0;
 #pragma unroll
-      for (int k = 0; k < GR; ++k) f[k] = fetch(base + 32 * G_NW * k, ee);
-#pragma unroll
-      for (int k = 0; k < GR; ++k) consume(f[k], i, lt, gt);
+    for (int k = 0; k < 2; ++k) {
+      const int b = 2 * lane + k;
+      cnt[k] = b < G_NBUCKET ? s_hist[b] : 0;
+      sum += cnt[k];
     }
-    s_slot[warp * 32 + lane] = make_float4(lt.x, lt.y, gt.x, gt.y);  // (consume ends with a __syncwarp: the slot is free)
+    if (lane == 0) { s_nhub = cnt[0]; s_nwide = cnt[1]; }
+    int run = warp_incl_scan(sum) - sum;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int b = 2 * lane + k;
+      if (b < G_NBUCKET) s_hist[b] = run;
+      run += cnt[k];
+    }
+  }
+  __syncthreads();
+  if (tid < TR) s_order[s_hist[bucket] + slot] = (uint8_t)tid;
+  __syncthreads();
+  const int n_hub = s_nhub, n_wide = s_nwide;
+  const int n_items = n_wide + ((TR - n_hub - n_wide + 7) >> 3);
+
+  // A fragments.  Row g of feature block mb = feature 8 g + 2 mb, row g + 8 = feature 8 g + 2 mb + 1: a lane ends up
+  // with the eight consecutive features 8 g ... 8 g + 7 of its rows = one 16-byte chunk of the operand image.
+  const float* wrow = t == 0 ? qv : t == 1 ? wg + WG_BETA : t == 2 ? wg + WG_DELTA : qv + F;  // row t of W
+  uint32_t aw[4][4];  // (hi f, hi f+1, lo f, lo f+1)
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float w = wrow[8 * g + 2 * mb + h];
+      aw[mb][h] = tf32_rna(w);
+      aw[mb][2 + h] = __float_as_uint(w - __uint_as_float(aw[mb][h]));  // (the tensor core reads the top 19 bits)
+    }
+
+  // Slab load.  The lane brings neighbours k = t, t + 4, ... of sub-row g: adjacency entry e0 + k * bs (while < e_end),
+  // then the neighbour's record; lane t = 0 also the record of node i_self (>= 0) into slot OCT_DEG.
+  auto load_slab = [&](int e0, int bs, int e_end, int i_self) {
+    int j[OCT_DEG / 4];
+#pragma unroll
+    for (int s = 0; s < OCT_DEG / 4; ++s) {
+      const int e = e0 + (t + 4 * s) * bs;
+      j[s] = e < e_end ? __ldg(col + e) : -1;
+    }
+    if (t == 0 && i_self >= 0) cp_async16(vrow + 4 * OCT_DEG, Srec + (uint64_t)(uint32_t)i_self * rec_bytes);
+#pragma unroll
+    for (int s = 0; s < OCT_DEG / 4; ++s)
+      if (j[s] >= 0) {
+        jrow[t + 4 * s] = j[s];
+        cp_async16(vrow + 4 * (t + 4 * s), Srec + (uint64_t)(uint32_t)j[s] * rec_bytes);
+      }
+    cp_async_wait_all();
+    __syncwarp();
+  };
+  float2 acc[4][2];  // [feature block][feature f / f + 1]: (column 2t, column 2t + 1)
+  auto block = [&](float val, bool add) {  // one MMA block: the lane's B entry is val (hi + lo parts)
+    const uint32_t bh = __float_as_uint(val) & 0xffffe000u;  // tf32 hi part by truncation; val - hi is exact
+    const uint64_t bbh = dup64(bh), bbl = dup64(__float_as_uint(val - __uint_as_float(bh)));
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      float d1[4], d[4];
+      mma_tf32(d1, aw[mb], bbh, zero);
+      mma_tf32(d, aw[mb], bbl, d1);
+      const float2 r0 = make_float2(fmaxf(d[0], 0.f), fmaxf(d[1], 0.f)), r1 = make_float2(fmaxf(d[2], 0.f), fmaxf(d[3], 0.f));
+      acc[mb][0] = add ? add2(acc[mb][0], r0) : r0;
+      acc[mb][1] = add ? add2(acc[mb][1], r1) : r1;
+    }
+  };
+  // nblk blocks (warp-uniform) out of the slab; the lane's sub-row has n_own neighbours, gated against node i_own
+  auto consume_slab = [&](int nblk, int n_own, int i_own) {
+#pragma unroll 2
+    for (int k = 0; k < nblk; ++k) {
+      const int j = jrow[k];
+      const float v = t == 3 ? 1.f : vrow[4 * k + t];
+      block(k < n_own ? v * (j < i_own ? g1 : g1c) : 0.f, true);
+    }
+    __syncwarp();
+  };
+  auto clear_acc = [&]() {
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) acc[mb][0] = acc[mb][1] = make_float2(0.f, 0.f);
+  };
+  // a row walked as eight interleaved sub-rows: slabs first, first + step, ... of its adjacency
+  auto walk_wide = [&](int eb, int deg, int first, int step, int i, bool with_self) {
+    clear_acc();
+    for (int e0 = eb + first * 8 * OCT_DEG; e0 < eb + deg; e0 += step * 8 * OCT_DEG) {
+      const int left = eb + deg - e0;  // entries from this slab on
+      load_slab(e0 + g, 8, eb + deg, with_self && g == 0 && e0 == eb ? i : -1);
+      consume_slab(min(OCT_DEG, (left + 7) >> 3), min(OCT_DEG, max(0, (left - g + 7) >> 3)), i);
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)  // the sixteen column sums of a feature -> acc[..][..].x of every lane
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v = acc[mb][h].x + acc[mb][h].y;
+        v += __shfl_xor_sync(FULL_MASK, v, 1);
+        v += __shfl_xor_sync(FULL_MASK, v, 2);
+        acc[mb][h].x = v;
+      }
+  };
+  auto store8 = [&](uint8_t* img, int r, bool second) {  // features 8 g ... 8 g + 7 of tile row r from acc (.x or .y)
+    float v[8];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      v[2 * mb] = second ? acc[mb][0].y : acc[mb][0].x;
+      v[2 * mb + 1] = second ? acc[mb][1].y : acc[mb][1].x;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(g ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(img + off) = hi;
+    *reinterpret_cast<uint4*>(img + TR * 128 + off) = lo;
+  };
+  // the rows' own records as one more block (gate 1, nothing summed): x1_i, c_i, d1_i.  r_col: the tile row of the lane's
+  // column (< 0: none), s_own: scalar t of its own record; r_a / r_b: tile rows of accumulator columns 2t, 2t + 1
+  auto finish = [&](int r_col, float s_own, int r_a, int r_b) {
+    if (r_a >= 0) store8(gA0, r_a, false);
+    if (r_b >= 0) store8(gA0, r_b, true);
+    if (r_col >= 0) {
+      if (t == 2) g_c[r_col] = s_own;
+      if (t == 3) g_d1[r_col] = s_own;
+    }
+    block(r_col < 0 ? 0.f : t == 3 ? 1.f : s_own, false);
+    if (r_a >= 0) store8(gA1, r_a, false);
+    if (r_b >= 0) store8(gA1, r_b, true);
+  };
+
+  // ---- work items dealt by a ticket: the wide rows first (longest work), then the octets in descending degree ----
+#pragma unroll 1
+  for (int item = warp; item < n_items;) {
+    if (item < n_wide) {
+      const int r = s_order[n_hub + item];
+      walk_wide(s_eb[r], s_dg[r], 0, 1, i0 + r, true);
+      const float s_own = vrow[4 * OCT_DEG + t];  // (sub-row 0 holds it; other lanes read a dead slot)
+      finish(g == 0 ? r : -1, s_own, t == 0 ? r : -1, -1);
+    } else {
+      const int base = n_hub + n_wide + 8 * (item - n_wide);
+      const int r = base + g < TR ? s_order[base + g] : -1;
+      const int i = i0 + r;
+      const int eb = r >= 0 ? s_eb[r] : 0, deg = r >= 0 ? s_dg[r] : 0;
+      const bool real = r >= 0 && i < node_end;
+      load_slab(eb, 1, eb + deg, real ? i : -1);
+      clear_acc();
+      consume_slab(__reduce_max_sync(FULL_MASK, deg), deg, i);
+      const float s_own = real ? vrow[4 * OCT_DEG + t] : 0.f;
+      finish(r, s_own, base + 2 * t < TR ? s_order[base + 2 * t] : -1, base + 2 * t + 1 < TR ? s_order[base + 2 * t + 1] : -1);
+    }
+    __syncwarp();
+    if (lane == 0) item = atomicAdd(&s_next, 1);
+    item = __shfl_sync(FULL_MASK, item, 0);
+  }
+  // ---- hub rows: slabs dealt over all warps of the CTA, partial sums added in warp order ----
+  for (int h = 0; h < n_hub; ++h) {
+    const int r = s_order[h], i = i0 + r;
+    walk_wide(s_eb[r], s_dg[r], warp, G_NW, i, false);
+    if (t == 0) {
+      s_part[warp][g][0] = make_float4(acc[0][0].x, acc[0][1].x, acc[1][0].x, acc[1][1].x);
+      s_part[warp][g][1] = make_float4(acc[2][0].x, acc[2][1].x, acc[3][0].x, acc[3][1].x);
+    }
     __syncthreads();
     if (warp == 0) {
-      float4 t = s_slot[lane];
-      for (int w = 1; w < G_NW; ++w) {
-        const float4 o = s_slot[w * 32 + lane];
-        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+      if (t == 0) {
+        float4 a = s_part[0][g][0], b = s_part[0][g][1];
+        for (int w = 1; w < G_NW; ++w) {
+          const float4 c = s_part[w][g][0], d = s_part[w][g][1];
+          a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+          b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+        }
+        acc[0][0].x = a.x; acc[0][1].x = a.y; acc[1][0].x = a.z; acc[1][1].x = a.w;
+        acc[2][0].x = b.x; acc[2][1].x = b.y; acc[3][0].x = b.z; acc[3][1].x = b.w;
       }
-      store_row(gA0, r, make_float2(g1 * t.x + (1.f - g1) * t.z, g1 * t.y + (1.f - g1) * t.w));
+      const float s_own = g == 0 ? __ldg(reinterpret_cast<const float*>(Srec + (uint64_t)(uint32_t)i * rec_bytes) + t) : 0.f;
+      finish(g == 0 ? r : -1, s_own, t == 0 ? r : -1, -1);
     }
     __syncthreads();
   }
@@ -620,21 +721,6 @@ static_assert(SMEM_BYTES <= 232448, "gossip tensor-core kernel exceeds the 227 K
 static_assert(SM_A0 % 1024 == 0 && SM_A1 % 1024 == 0 && IMG_W2 % 1024 == 0 && IMG_P1 % 1024 == 0 && IMG_P2 % 1024 == 0,
               "UMMA tiles must be 1024-B aligned");
 static_assert(SM_CD % 16 == 0 && TILE_BYTES % 16 == 0, "bulk copies need 16-byte alignment");
-
-// 8 consecutive fp32 -> one 16-byte chunk of bf16 hi and one of lo
-__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 f = __bfloat1622float2(hh);
-    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
 
 // phase timing (thread 0 of every CTA adds its clock64 deltas; read with desco_gossip_tc_phase_cycles)
 enum { GPH_LOAD = 0, GPH_X2, GPH_Y1, GPH_Y2, GPH_Y4, GPH_SPARE, GPH_COUNT };
