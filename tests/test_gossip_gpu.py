@@ -170,3 +170,41 @@ def test_gossip_hub_rows_take_the_whole_cta_paths(cuda_device, precision):
         ref = om.graph_to_count(x.double(), torch.from_numpy(csr.edge_index())).float()
     out = _run(pm, csr, x, qe)
     assert _rel(out, ref) <= TOL
+
+
+def test_gossip_gather_degree_classes(cuda_device):
+    """The tensor-path gather sorts a 128-row tile by degree class: rows of up to 32 neighbours go through octets (eight rows
+    per MMA block), longer rows are walked alone as eight interleaved sub-rows, rows beyond one slab (256 entries here: two
+    slabs up to 512, then the whole CTA) take several slabs.  A graph with rows sitting exactly on those boundaries (0, 1,
+    7, 8, 9, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1100 neighbours), spread over tiles that are not full, Q = 5 so that
+    a query group is ragged; fp64 oracle."""
+    import networkx as nx
+
+    from desco_b200.graph import csr_from_networkx
+
+    om, pm = _pair(21, "bf16x3")
+    n = 128 * 11 + 37
+    g = nx.empty_graph(n)
+    rng = np.random.default_rng(4)
+    degs = [0, 1, 7, 8, 9, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1100]
+    centres = rng.choice(n, size=len(degs), replace=False)
+    for c, d in zip(centres, degs):
+        others = rng.choice(np.setdiff1d(np.arange(n), centres), size=d, replace=False)
+        g.add_edges_from((int(c), int(v)) for v in others)
+    csr = csr_from_networkx([g])
+    have = set(np.diff(csr.rowptr)[centres].tolist())
+    assert have == set(degs)
+    gen = torch.Generator().manual_seed(9)
+    Q = 5
+    x = torch.floor(torch.exp(torch.randn(csr.num_nodes, Q, generator=gen)))
+    qe = torch.randn(Q, 64, generator=gen)
+    om = om.double()
+    om.set_query_emb(qe.double())
+    with torch.no_grad():
+        ref = om.graph_to_count(x.double(), torch.from_numpy(csr.edge_index())).float()
+    out = _run(pm, csr, x, qe)
+    assert _rel(out, ref) <= TOL
+    # the same rows through the fp32 FFMA kernel of the library: the two paths only differ in rounding
+    pm.emb_model.precision = "fp32"
+    out32 = _run(pm, csr, x, qe)
+    assert _rel(out, out32) <= TOL
