@@ -68,6 +68,10 @@ def _tensor_peak():
     return 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def _num_sms(torch):
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
 def build_workload(seed: int):
     from desco_b200.graph import first_nonempty_centres, gen_enzymes_shaped
 
@@ -354,9 +358,12 @@ def run_gossip_leg(ctx, args, model):
                      "peak_source": tsrc, "traffic": None,
                      "note": "USEFUL fp32-equivalent flops of the four GEMMs (the kernel issues 3x as many bf16 flops for the "
                              "hi/lo split) over the chain kernel's own CUDA-event time"},
-        "gather": {"kernel": "gossip_gather_kernel", "bound": "issue (scalar fp32 recompute of the neighbours' rows; ncu: issue "
-                                                               "active 74 %)", "ms_per_step": gather_ms,
-                   "edge_query_pairs_per_s": M * Q / (gather_ms * 1e-3)},
+        "gather": {"kernel": "gossip_gather_kernel",
+                   "bound": "warp-level tensor pipe + issue: the neighbours' rows are recomputed as tf32 mma.sync blocks (8 "
+                            "neighbour records x 64 features = 8 HMMA.1688 at 8.6 cycles each per sub-partition) with relu + add "
+                            "on the CUDA cores; profiles/r2_gossip_gather_ablation.txt",
+                   "ms_per_step": gather_ms, "edge_query_pairs_per_s": M * Q / (gather_ms * 1e-3),
+                   "mma_blocks_floor_ms": (M * Q / 8.0) * 8 * 8.6 / (4 * _num_sms(torch) * 1.965e9) * 1e3},
         "reference_formulation_bytes_per_step": alg,
         "note": "the reference formulation moves a 64-wide fp32 row per edge and query; these kernels move 16 B per edge and "
                 "query and recompute the row, so bytes / time against that formulation is not a roofline and is not reported",
