@@ -370,6 +370,36 @@ def run_gossip_leg(ctx, args, model):
     }
 
 
+def replicate_inputs(ctx, tensors, what):
+    """The target CSR and the counts are generated on every rank from the same seeds.  Check that the copies really are
+    bit-identical (sizes + two digests per tensor, all-gathered) and, if any rank's differs, take rank 0's: a
+    strong-scaling job shards ONE input.  Returns (tensors, what was found)."""
+    torch, dist, dev = ctx.torch, ctx.dist, ctx.dev
+    if ctx.world == 1:
+        return tensors, {"what": what, "checked": False}
+
+    def digest(t):
+        v = t.contiguous().view(-1).view(torch.int32).to(torch.int64)
+        w = (torch.arange(v.numel(), device=dev, dtype=torch.int64) % 65521) + 1
+        return [int(t.numel()), int(v.sum().item()), int((v * w).sum().item())]
+
+    sig = torch.tensor([d for t in tensors for d in digest(t)], dtype=torch.int64, device=dev)
+    allsig = [torch.zeros_like(sig) for _ in range(ctx.world)]
+    dist.all_gather(allsig, sig)
+    differing = [r for r in range(ctx.world) if not torch.equal(allsig[r], allsig[0])]
+    if differing:
+        out = []
+        for i, t in enumerate(tensors):
+            n0 = int(allsig[0][3 * i].item())
+            if t.dim() == 1 and t.numel() != n0:
+                t = torch.empty(n0, dtype=t.dtype, device=dev)
+            dist.broadcast(t, 0)
+            out.append(t)
+        tensors = out
+    return tensors, {"what": what, "checked": True, "ranks_whose_generated_copy_differed_from_rank0": differing,
+                     "action": "rank 0's copy broadcast to all ranks" if differing else "none"}
+
+
 def config5_name(args):
     return f"powerlaw_chunglu_{args.c5_nodes}nodes_{args.c5_edges}undirected_edges_depth2_x29queries"
 
@@ -382,7 +412,8 @@ def run_config5(ctx, args, nm, steps, warmup):
     from desco_b200.lightning_model import GossipCountingModel
 
     depth = 2
-    g = gen_powerlaw_device(args.c5_nodes, args.c5_edges, seed=0, device=dev)  # same seed: the CSR is replicated
+    g = gen_powerlaw_device(args.c5_nodes, args.c5_edges, seed=0, device=dev)  # same seed: the CSR is replicated ...
+    (g.rowptr, g.col), rep_graph = replicate_inputs(ctx, [g.rowptr, g.col], "target CSR")  # ... and checked to be
     N, M = g.num_nodes, g.num_directed_edges
     torch.manual_seed(1)
     gm = GossipCountingModel().eval().to(dev)
@@ -424,6 +455,8 @@ def run_config5(ctx, args, nm, steps, warmup):
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)
     x = torch.floor(torch.exp(torch.randn((N, Q), device=dev, generator=gen)))  # replicated hand-off of the counting stage
+    (x,), rep_x = replicate_inputs(ctx, [x], "counts x[N, Q]")
+    replicated = [rep_graph, rep_x]
 
     def step():
         with torch.no_grad():
@@ -480,6 +513,26 @@ def run_config5(ctx, args, nm, steps, warmup):
             single_ms = sum(p.elapsed_time(q) for p, q in evs) / len(evs)
         sharded_equals_single = bool(torch.equal(ref_out, out))
         sharded_vs_single = float(((ref_out - out).abs() / ref_out.abs().clamp(min=1.0)).max().item())
+        if not sharded_equals_single:  # say where: which rows, whose, how many queries
+            dd = (ref_out - out).abs() / ref_out.abs().clamp(min=1.0)
+            bad = (dd > 0).nonzero()
+            rows = torch.unique(bad[:, 0])
+            deg = g.rowptr[1:] - g.rowptr[:-1]
+            print(f"[bench] sharded != single: {bad.shape[0]} entries in {rows.numel()} rows", file=sys.stderr)
+            for r in rows[:16].tolist():
+                qs = bad[bad[:, 0] == r][:, 1].tolist()
+                print(f"[bench]   row {r} deg {int(deg[r])} owner {r // plan.n_loc} off {r % plan.n_loc} queries {qs[:12]} "
+                      f"err {dd[r].max().item():.3e} sharded {out[r, qs[0]].item():.6f} single {ref_out[r, qs[0]].item():.6f}", file=sys.stderr)
+            gm.emb_model.precision = "fp32"
+            ref32 = single()
+            gm.emb_model.precision = "bf16x3"
+            for r in rows[:25].tolist():
+                nb = g.col[int(g.rowptr[r]):int(g.rowptr[r + 1])]
+                print(f"[bench]   row {r}: |sharded - fp32 path| {(out[r] - ref32[r]).abs().max().item():.3e}  |single - fp32 path| "
+                      f"{(ref_out[r] - ref32[r]).abs().max().item():.3e}  neighbour degrees {sorted(deg[nb.long()].tolist())[-4:]} "
+                      f"neighbours among the bad rows {int(torch.isin(nb.long(), rows).sum())}", file=sys.stderr)
+            again = single()
+            print(f"[bench]   single forward repeated equals itself: {bool(torch.equal(again, ref_out))}", file=sys.stderr)
         del ref_out
     ctx.barrier()
 
@@ -497,7 +550,7 @@ def run_config5(ctx, args, nm, steps, warmup):
     mm_flops = 2.0 * (128 * 64 + 128 * 64 + 64 * 64 + 64 * 256) * N * Q / world  # per rank
     return {
         "workload": config5_name(args), "nodes": N, "directed_edges": M, "queries": Q, "depth": depth, "n_gpus": world,
-        "scaling": "strong", "csr": "replicated on every GPU",
+        "scaling": "strong", "csr": "replicated on every GPU", "inputs_replicated_check": replicated,
         "partition_count": {
             "what": "canonical partition + SHMP typing + SHMP counting (29 queries) of a fixed seeded centre sample, dealt "
                     "over the ranks by estimated work (ShardedPipeline.deal_centres; a full sweep uses the contiguous "

@@ -128,6 +128,23 @@ def _worker(rank, world, port, q):
             work.wait()
             for r in range(world):
                 assert torch.all(full[r * plan.n_loc:(r + 1) * plan.n_loc] == 10 * (r + 1) + gi)
+        # bench.py's replicated-input check: a rank whose generated copy differs (here: another size, another value)
+        # gets rank 0's; identical copies are left alone
+        import sys
+        import types
+
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+
+        bctx = types.SimpleNamespace(torch=torch, dist=dist, dev=torch.device("cpu"), world=world, rank=rank)
+        col = torch.arange(20 if rank == 0 else 22, dtype=torch.int32)
+        (rp, c2), info = bench.replicate_inputs(bctx, [torch.arange(11, dtype=torch.int32), col], "csr")
+        assert info["ranks_whose_generated_copy_differed_from_rank0"] == [1] and torch.equal(c2, torch.arange(20, dtype=torch.int32))
+        xr = torch.ones(10, 29) + (0.0 if rank == 0 else 1e-3)
+        (x2,), info = bench.replicate_inputs(bctx, [xr], "x")
+        assert info["ranks_whose_generated_copy_differed_from_rank0"] == [1] and torch.equal(x2, torch.ones(10, 29))
+        (y2,), info = bench.replicate_inputs(bctx, [torch.ones(5, 3)], "y")
+        assert info["ranks_whose_generated_copy_differed_from_rank0"] == [] and info["action"] == "none"
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
