@@ -386,8 +386,9 @@ __global__ void __launch_bounds__(THREADS, 2) gossip_layer1_kernel(
 // dense GEMM (x2: 128->64, y1: 128->64, y2: 64->64, y3: 64->256) against a few hundred flops of gather, so the FFMA
 // kernel above is compute bound on the CUDA cores.  Here the work is split by what bounds it:
 //   * gossip_gather_kernel - the gated sweep (dependent col[] -> S4[] loads, ~1 us each): small CTAs at high occupancy.
-//     A CTA owns a tile = 128 consecutive nodes x 1 query, recomputes x1_j per neighbour and writes the tile's u and x1
-//     rows to a staging buffer AS the bf16 hi/lo SWIZZLE_128B operand images the tensor core wants (64 KB per tile);
+//     A CTA owns a tile = 128 consecutive nodes x 1 query, recomputes x1_j per neighbour (warp-level tf32 MMA blocks,
+//     see the kernel) and writes the tile's u and x1 rows to a staging buffer AS the bf16 hi/lo SWIZZLE_128B operand
+//     images the tensor core wants (64 KB per tile);
 //   * gossip_chain_kernel - persistent, one CTA per SM: the four weight matrices stay resident in shared memory as
 //     operand images (144 KB, bulk-copied once), a tile's two operand slots arrive by bulk async copy (the next tile's
 //     are issued as soon as a slot is dead, under the running tile's epilogues), the four GEMMs run on tcgen05 (M = 128,
