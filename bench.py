@@ -68,6 +68,21 @@ def _tensor_peak():
     return 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def gather_roofline(nodes, directed_edges, queries, world, gather_ms):
+    """HBM roofline of gossip_gather_kernel on the bytes its own formulation has to move (per rank and forward): a
+    16-byte record + a 4-byte adjacency entry per (edge, query) read, and the tile's operand images (u and x1 as bf16 hi /
+    lo rows + c + d1 = 520 B per (node, query)) written for the chain kernel.  Pure function: tests/test_bench_contract_cpu.py."""
+    peak, src = _peaks()
+    alg = (20.0 * directed_edges * queries + 520.0 * nodes * queries) / max(world, 1)
+    ach = alg / (gather_ms * 1e-3) / 1e9 if gather_ms > 0 else 0.0
+    return {"kernel": "gossip_gather_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "peak_source": src, "algorithmic_bytes_per_step_per_rank": alg, "ms_per_step": gather_ms,
+            "traffic": None,
+            "note": "bytes of the kernel's OWN formulation (records are re-read across tiles through L2, so DRAM traffic is "
+                    "lower: ncu 0.88 GB per 8192-tile launch, profiles/r2_ncu_gossip_gather_summary.txt); what bounds the "
+                    "kernel is the warp-level tensor pipe + issue, profiles/r2_gossip_gather_ablation.txt"}
+
+
 def _num_sms(torch):
     return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
 
@@ -363,6 +378,7 @@ def run_gossip_leg(ctx, args, model):
                             "neighbour records x 64 features = 8 HMMA.1688 at 8.6 cycles each per sub-partition) with relu + add "
                             "on the CUDA cores; profiles/r2_gossip_gather_ablation.txt",
                    "ms_per_step": gather_ms, "edge_query_pairs_per_s": M * Q / (gather_ms * 1e-3),
+                   "roofline": gather_roofline(N, M, Q, 1, gather_ms),
                    "mma_blocks_floor_ms": (M * Q / 8.0) * 8 * 8.6 / (4 * _num_sms(torch) * 1.965e9) * 1e3},
         "reference_formulation_bytes_per_step": alg,
         "note": "the reference formulation moves a 64-wide fp32 row per edge and query; these kernels move 16 B per edge and "
@@ -573,6 +589,7 @@ def run_config5(ctx, args, nm, steps, warmup):
             "stage_ms_per_step": {"layer0_scalar_sweep": l0_ms, "layer1_gated_sweep_gather": gather_ms,
                                   "layer1_postmp_tcgen05_chain": chain_ms, "timed_in": "extra profiled steps, max over ranks"},
             "single_gpu_ms_same_job": single_ms,
+            "roofline_gather": gather_roofline(N, M, Q, world, gather_ms),
             "roofline": {"kernel": "gossip_chain_kernel", "bound": "tensor", "unit": "TFLOP/s",
                          "achieved": mm_flops / (chain_ms * 1e-3) / 1e12, "peak": tpeak,
                          "frac": mm_flops / (chain_ms * 1e-3) / 1e12 / tpeak, "peak_source": tsrc, "traffic": None,

@@ -22,3 +22,17 @@ def test_reference_arm_prints_the_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_gather_roofline_arithmetic():
+    """bench.gather_roofline: bytes of the gather's own formulation per rank over its time, against the measured HBM peak."""
+    import bench
+
+    r = bench.gather_roofline(nodes=1_000_000, directed_edges=22_000_000, queries=29, world=1, gather_ms=11.8)
+    alg = 20.0 * 22_000_000 * 29 + 520.0 * 1_000_000 * 29
+    assert r["algorithmic_bytes_per_step_per_rank"] == alg and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["achieved"] - alg / 11.8e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 0.2 < r["frac"] < 0.6
+    r8 = bench.gather_roofline(10_000_000, 220_000_000, 29, 8, 17.4)
+    assert abs(r8["algorithmic_bytes_per_step_per_rank"] - (20.0 * 220e6 * 29 + 520.0 * 10e6 * 29) / 8) < 1.0
+    assert bench.gather_roofline(1, 1, 1, 1, 0.0)["achieved"] == 0.0
