@@ -11,13 +11,32 @@ anything else raises at construction and the caller keeps using the eager path.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
 from .data import MODE_HETERO, DeviceCSR, LARGE_GRAPH_NODES, _ptr, partition_batch
 from .gnn_model import PRECISION, TILE_ROWS
+
+
+def pack_int32_block(arrays: Sequence, align: int = 128) -> Tuple[torch.Tensor, List[Tuple[int, int]]]:
+    """Lay int32 arrays (the CSR parts and the centre list of a step) out back to back in ONE host buffer - pinned when
+    CUDA is there - every part starting on a multiple of ``align`` elements.  The same layout on the device (``.to(device)``,
+    then ``block[o:o + n]`` views as the step's CSR and centre storage) lets a single host->device copy refresh everything
+    the step reads, instead of one copy per array.  Returns ``(block, [(offset, length), ...])``."""
+    parts, total = [], 0
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        if a.dtype != np.int32 or a.ndim != 1:
+            raise ValueError("pack_int32_block takes one-dimensional int32 arrays")
+        parts.append((total, int(a.shape[0])))
+        total += -(-int(a.shape[0]) // align) * align
+    block = torch.zeros(max(total, 1), dtype=torch.int32, pin_memory=torch.cuda.is_available())
+    for (o, n), a in zip(parts, arrays):
+        block[o:o + n] = torch.from_numpy(np.ascontiguousarray(a))
+    return block, parts
 
 
 class NeighborhoodCountStep:
@@ -27,7 +46,9 @@ class NeighborhoodCountStep:
     A step whose neighborhoods outgrow the capacities reports ENOBUFS/ERANGE through ``result()``."""
 
     def __init__(self, model, graph: DeviceCSR, example_centres: torch.Tensor, depth: int, margin: float = 1.5,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, centres_storage: Optional[torch.Tensor] = None):
+        """``centres_storage``: caller-owned int32 [C] device tensor the step reads its centres from (instead of a
+        private copy) - e.g. a view of the block ``pack_int32_block`` describes, next to the CSR it is copied with."""
         if graph.max_graph_nodes > LARGE_GRAPH_NODES:
             raise NotImplementedError("the stream-ordered step serves the small-graph partition kernels")
         emb = model.emb_model
@@ -44,7 +65,15 @@ class NeighborhoodCountStep:
         self.cap_rows = int(max(probe.num_rows, 64) * margin) + 64
         self.cap_edges = int(max(probe.num_edges, 64) * margin) + 64
         i32 = dict(dtype=torch.int32, device=dev)
-        self.centres = centres.clone()
+        if centres_storage is not None:
+            if (centres_storage.dtype != torch.int32 or centres_storage.numel() != C or centres_storage.device != dev
+                    or not centres_storage.is_contiguous()):
+                raise ValueError(f"centres_storage must be a contiguous int32 [{C}] tensor on {dev}")
+            if centres_storage.data_ptr() != centres.data_ptr():
+                centres_storage.copy_(centres)
+            self.centres = centres_storage
+        else:
+            self.centres = centres.clone()
         self.nbh_ptr = torch.zeros(C + 1, **i32)
         self.centre_out = torch.zeros(C, **i32)
         self.centre_graph = torch.zeros(C, **i32)

@@ -36,3 +36,19 @@ def test_gather_roofline_arithmetic():
     r8 = bench.gather_roofline(10_000_000, 220_000_000, 29, 8, 17.4)
     assert abs(r8["algorithmic_bytes_per_step_per_rank"] - (20.0 * 220e6 * 29 + 520.0 * 10e6 * 29) / 8) < 1.0
     assert bench.gather_roofline(1, 1, 1, 1, 0.0)["achieved"] == 0.0
+
+
+def test_pack_int32_block_layout():
+    """pipeline.pack_int32_block: parts back to back, each on an aligned offset, contents intact, int32 only."""
+    import numpy as np
+    import pytest
+
+    from desco_b200.pipeline import pack_int32_block
+
+    arrs = [np.arange(5, dtype=np.int32), np.arange(300, dtype=np.int32) * 3, np.zeros(0, dtype=np.int32), np.array([7], dtype=np.int32)]
+    block, parts = pack_int32_block(arrs, align=128)
+    assert parts == [(0, 5), (128, 300), (512, 0), (512, 1)] and block.numel() == 640
+    for (o, n), a in zip(parts, arrs):
+        assert np.array_equal(block[o:o + n].numpy(), a)
+    with pytest.raises(ValueError):
+        pack_int32_block([np.arange(3, dtype=np.int64)])
