@@ -691,6 +691,10 @@ def run_ours(args):
                            "precision": "bf16x3 tcgen05 GEMM chain, fp32 accumulate (1e-4 parity path)",
                            "n1_base": "the N = 1 line of bench.py is BASELINE configs[1] (config 2); the 1-GPU time of THIS workload "
                                       "is config5.gossip.single_gpu_ms_same_job here and config5.gossip.ms_per_step of the N = 1 line"},
+                "value_n1_same_workload": (c5["nodes"] / (gs["single_gpu_ms_same_job"] * 1e-3)
+                                           if gs.get("single_gpu_ms_same_job") else None),
+                "value_n1_note": "this workload on ONE GPU, measured in this job on rank 0 (the N = 1 bench line is config 2, another "
+                                 "metric): strong-scaling efficiency = value / (n_gpus * value_n1_same_workload)",
                 "e2e": gs["e2e"], "gpu_launches": gs["gpu_launches_rank0"], "clocks": clocks, "roofline": gs["roofline"],
                 "cpu_baseline": None, "config5": c5, "parity": c5["parity"],
             }
