@@ -61,3 +61,58 @@ def test_absent_neighbour_slots_add_exactly_zero():
     assert not z.any()
     acc = np.float32(1.2345678) + np.maximum(z, 0)
     assert (acc == np.float32(1.2345678)).all()
+
+
+def test_tile_decomposition_covers_every_neighbour_once():
+    """The index arithmetic of gossip_gather_kernel's work decomposition, restated: a 128-row tile is split into hub rows
+    (> 512 neighbours, slabs of 256 dealt over the CTA's warps), wide rows (33..512, eight interleaved sub-rows, slabs of
+    256) and octets of <= 32-neighbour rows in descending degree; every adjacency entry of every row must be visited
+    exactly once and the per-sub-row counts the kernel derives must add up."""
+    TR, OCT, HUB, NW = 128, 32, 512, 4
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        deg = np.minimum((rng.pareto(1.2, TR) * 6).astype(np.int64), 3000)
+        deg[rng.integers(0, TR, 5)] = [0, 32, 33, 512, 513]
+        bucket = np.where(deg > HUB, 0, np.where(deg > OCT, 1, 2 + OCT - deg))
+        order = np.argsort(bucket, kind="stable")  # any order inside a bucket (the kernel's is atomic-slot order)
+        n_hub, n_wide = int((bucket == 0).sum()), int((bucket == 1).sum())
+        n_items = n_wide + (TR - n_hub - n_wide + 7) // 8
+        seen = [np.zeros(d, dtype=np.int64) for d in deg]
+        rows_done = np.zeros(TR, dtype=np.int64)
+        for item in range(n_items):
+            if item < n_wide:
+                r = order[n_hub + item]
+                d = int(deg[r])
+                e0 = 0
+                while e0 < d:  # walk_wide(first = 0, step = 1)
+                    left = d - e0
+                    nblk = min(OCT, (left + 7) >> 3)
+                    for g in range(8):
+                        n_own = min(OCT, max(0, (left - g + 7) >> 3))
+                        assert n_own <= nblk
+                        for k in range(n_own):
+                            seen[r][e0 + g + 8 * k] += 1
+                    e0 += 8 * OCT
+                rows_done[r] += 1
+            else:
+                base = n_hub + n_wide + 8 * (item - n_wide)
+                rows = [order[base + g] for g in range(8) if base + g < TR]
+                nblk = max(int(deg[r]) for r in rows)
+                assert nblk <= OCT
+                for r in rows:
+                    seen[r][:int(deg[r])] += 1
+                    rows_done[r] += 1
+        for h in range(n_hub):
+            r = order[h]
+            d = int(deg[r])
+            for warp in range(NW):  # walk_wide(first = warp, step = NW)
+                e0 = warp * 8 * OCT
+                while e0 < d:
+                    left = d - e0
+                    for g in range(8):
+                        for k in range(min(OCT, max(0, (left - g + 7) >> 3))):
+                            seen[r][e0 + g + 8 * k] += 1
+                    e0 += NW * 8 * OCT
+            rows_done[r] += 1
+        assert (rows_done == 1).all()
+        assert all((s == 1).all() for s in seen)
