@@ -147,7 +147,7 @@ def run_reference(args):
         return
     import torch
 
-    if world > 1:  # the multi-GPU arm's workload: gossip over the power-law target, CPU oracle on a bounded sample
+    if world > 1 or args.gpus > 1:  # the multi-GPU arm's workload: gossip over the power-law target, CPU oracle on a bounded sample
         csr, og, x, ei = cpu_gossip_workload()
         times = []
         for i in range(args.warmup + args.steps):
